@@ -1,0 +1,358 @@
+// ops.cuh -- per-pair physics of the Newtonian kernels, written for the pair engine.
+//
+// Each Op states which reference kernel it replaces (file:line in tupan/lib/src) and the
+// reference's own flops-per-pair convention (its "Total flop count" comments), which is the
+// convention bench.py reports rooflines in.  The arithmetic is arranged for the GPU (FMA
+// chains, rsqrt seed + one cubic step, masks kept in predicates) and therefore differs from
+// the reference in rounding, not in meaning: results agree to ~1e-15 per pair (fp64).
+//
+// Caller array order (libtupan.h): 8-array kernels pass  m, rx, ry, rz, e2, vx, vy, vz.
+#pragma once
+#include "pair_engine.cuh"
+
+namespace tupan {
+
+struct NoParams {};
+
+// Packed row layouts (shared by several kernels so one packed buffer / one all-gather can
+// feed them all).
+//   Row5 : rx ry rz m  e2                      (phi, acc)
+//   Row8 : rx ry rz m  vx vy vz e2             (acc_jerk, tstep, pnacc, nreg_X, sakura)
+//   Row14: Row8 + ax ay az jx jy jz            (snap_crackle)
+//   RowV : vx vy vz m  ax ay az                (nreg_V)
+enum { JX = 0, JY = 1, JZ = 2, JM = 3 };
+enum { J5_E2 = 4 };
+enum { J8_VX = 4, J8_VY = 5, J8_VZ = 6, J8_E2 = 7 };
+enum { J14_AX = 8, J14_AY = 9, J14_AZ = 10, J14_JX = 11, J14_JY = 12, J14_JZ = 13 };
+
+template <typename T, int NJP>
+TUPAN_DEV void pack_row5(const T* const* j, long long r, T (&row)[NJP])
+{
+    row[JM] = j[0][r]; row[JX] = j[1][r]; row[JY] = j[2][r]; row[JZ] = j[3][r]; row[J5_E2] = j[4][r];
+}
+template <typename T, int NJP>
+TUPAN_DEV void pack_row8(const T* const* j, long long r, T (&row)[NJP])
+{
+    row[JM] = j[0][r]; row[JX] = j[1][r]; row[JY] = j[2][r]; row[JZ] = j[3][r];
+    row[J8_E2] = j[4][r]; row[J8_VX] = j[5][r]; row[J8_VY] = j[6][r]; row[J8_VZ] = j[7][r];
+}
+
+template <typename T, int NA>
+TUPAN_DEV void sum_combine(T (&a)[NA], const T (&b)[NA])
+{
+#pragma unroll
+    for (int k = 0; k < NA; ++k) a[k] += b[k];
+}
+template <typename T, int NA>
+TUPAN_DEV void zero_all(T (&a)[NA])
+{
+#pragma unroll
+    for (int k = 0; k < NA; ++k) a[k] = T(0);
+}
+
+// =======================================================================================
+// phi  -- replaces phi_kernel (phi_kernel.c:5-35, core phi_kernel_common.h:7-32); 14 flop/pair
+// =======================================================================================
+template <typename T> struct PhiOp {
+    typedef T real;
+    typedef NoParams Params;
+    enum { NI = 4, NJ = 5, NA = 1, NO = 1, WPT = 4, UNROLL = 4 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IX, IY, IZ, IE };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row5(j, r, row); }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
+    {
+        T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
+        T x = s[IE] + row[J5_E2];
+        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        a[0] = fma(-row[JM], w.r1, a[0]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
+    static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
+    {
+        out[0][i] = a[0];
+    }
+};
+
+// =======================================================================================
+// acc  -- replaces acc_kernel (acc_kernel.c:5-41, core acc_kernel_common.h:7-38); 20 flop/pair
+// =======================================================================================
+template <typename T> struct AccOp {
+    typedef T real;
+    typedef NoParams Params;
+    enum { NI = 4, NJ = 5, NA = 3, NO = 3, WPT = 4, UNROLL = 4 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IX, IY, IZ, IE };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row5(j, r, row); }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
+    {
+        T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
+        T x = s[IE] + row[J5_E2];
+        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        T g = row[JM] * w.r3;
+        a[0] = fma(-g, rx, a[0]); a[1] = fma(-g, ry, a[1]); a[2] = fma(-g, rz, a[2]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
+    static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
+    {
+        out[0][i] = a[0]; out[1][i] = a[1]; out[2][i] = a[2];
+    }
+};
+
+// =======================================================================================
+// acc_jerk -- replaces acc_jerk_kernel (acc_jerk_kernel.c:5-61, core
+// acc_jerk_kernel_common.h:7-56); 42 flop/pair by the reference's count.
+// FP64-pipe instructions per pair here: 6 (differences) + 4 (r2+e2) + 3 (r.v) + 5 (rsqrt
+// step) + 2 (1/r^2, 1/r^3) + 2 (alpha) + 1 (m/r^3) + 9 (FMA updates) = 32.
+// =======================================================================================
+template <typename T> struct AccJerkOp {
+    typedef T real;
+    typedef NoParams Params;
+    enum { NI = 7, NJ = 8, NA = 6, NO = 6, WPT = 2, UNROLL = 4 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IX, IY, IZ, IE, IVX, IVY, IVZ };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
+        s[IVX] = a[5][i]; s[IVY] = a[6][i]; s[IVZ] = a[7][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row8(j, r, row); }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
+    {
+        T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
+        T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
+        T x = s[IE] + row[J8_E2];
+        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
+        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        T alpha = (T(3) * w.r2) * rv;
+        vx = fma(-alpha, rx, vx); vy = fma(-alpha, ry, vy); vz = fma(-alpha, rz, vz);
+        T g = row[JM] * w.r3;
+        a[0] = fma(-g, rx, a[0]); a[1] = fma(-g, ry, a[1]); a[2] = fma(-g, rz, a[2]);
+        a[3] = fma(-g, vx, a[3]); a[4] = fma(-g, vy, a[4]); a[5] = fma(-g, vz, a[5]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
+    static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
+    {
+#pragma unroll
+        for (int k = 0; k < NO; ++k) out[k][i] = a[k];
+    }
+};
+
+// =======================================================================================
+// snap_crackle -- replaces snap_crackle_kernel (snap_crackle_kernel.c:5-83, core
+// snap_crackle_kernel_common.h:7-95); 114 flop/pair.
+// Caller arrays: m rx ry rz e2 vx vy vz ax ay az jx jy jz.
+// =======================================================================================
+template <typename T> struct SnapCrackleOp {
+    typedef T real;
+    typedef NoParams Params;
+    enum { NI = 13, NJ = 14, NA = 6, NO = 6, WPT = 1, UNROLL = 2 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IX, IY, IZ, IE, IVX, IVY, IVZ, IAX, IAY, IAZ, IJX, IJY, IJZ };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
+        s[IVX] = a[5][i]; s[IVY] = a[6][i]; s[IVZ] = a[7][i];
+        s[IAX] = a[8][i]; s[IAY] = a[9][i]; s[IAZ] = a[10][i];
+        s[IJX] = a[11][i]; s[IJY] = a[12][i]; s[IJZ] = a[13][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP])
+    {
+        pack_row8(j, r, row);
+        row[J14_AX] = j[8][r]; row[J14_AY] = j[9][r]; row[J14_AZ] = j[10][r];
+        row[J14_JX] = j[11][r]; row[J14_JY] = j[12][r]; row[J14_JZ] = j[13][r];
+    }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
+    {
+        T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
+        T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
+        T ax = s[IAX] - row[J14_AX], ay = s[IAY] - row[J14_AY], az = s[IAZ] - row[J14_AZ];
+        T jx = s[IJX] - row[J14_JX], jy = s[IJY] - row[J14_JY], jz = s[IJZ] - row[J14_JZ];
+        T x = s[IE] + row[J8_E2];
+        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
+        T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
+        T rj = rx * jx; rj = fma(ry, jy, rj); rj = fma(rz, jz, rj);
+        T ra = rx * ax; ra = fma(ry, ay, ra); ra = fma(rz, az, ra);
+        T va = vx * ax; va = fma(vy, ay, va); va = fma(vz, az, va);
+        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+
+        // same recurrences as snap_crackle_kernel_common.h:63-84
+        T alpha = rv * w.r2;
+        T alpha2 = alpha * alpha;
+        T beta = T(3) * fma(v2 + ra, w.r2, alpha2);
+        T gamma = fma(fma(T(3), va, rj), w.r2, alpha * fma(T(-4), alpha2, beta));
+        alpha *= T(3);
+        gamma *= T(3);
+        vx = fma(-alpha, rx, vx); vy = fma(-alpha, ry, vy); vz = fma(-alpha, rz, vz);
+        T a2 = T(2) * alpha;
+        ax -= fma(a2, vx, beta * rx); ay -= fma(a2, vy, beta * ry); az -= fma(a2, vz, beta * rz);
+        alpha *= T(3);
+        beta *= T(3);
+        jx -= fma(alpha, ax, fma(beta, vx, gamma * rx));
+        jy -= fma(alpha, ay, fma(beta, vy, gamma * ry));
+        jz -= fma(alpha, az, fma(beta, vz, gamma * rz));
+        T g = row[JM] * w.r3;
+        a[0] = fma(-g, ax, a[0]); a[1] = fma(-g, ay, a[1]); a[2] = fma(-g, az, a[2]);
+        a[3] = fma(-g, jx, a[3]); a[4] = fma(-g, jy, a[4]); a[5] = fma(-g, jz, a[5]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
+    static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
+    {
+#pragma unroll
+        for (int k = 0; k < NO; ++k) out[k][i] = a[k];
+    }
+};
+
+// =======================================================================================
+// tstep -- replaces tstep_kernel (tstep_kernel.c:5-50, core tstep_kernel_common.h:7-60);
+// 42 flop/pair.  Two accumulators: sum and max of the pair frequency w2; the epilogue
+// eta/sqrt(1+.) is tstep_kernel.c:46-47.  The lane/chunk reduction of the second
+// accumulator is a max, as is the fused minimum time-step (see finish_min in api).
+// =======================================================================================
+template <typename T> struct TstepParams { T eta; };
+template <typename T> struct TstepOp {
+    typedef T real;
+    typedef TstepParams<T> Params;
+    enum { NI = 8, NJ = 8, NA = 2, NO = 2, WPT = 2, UNROLL = 4 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IX, IY, IZ, IE, IVX, IVY, IVZ, IM };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IM] = a[0][i];
+        s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
+        s[IVX] = a[5][i]; s[IVY] = a[6][i]; s[IVZ] = a[7][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row8(j, r, row); }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p)
+    {
+        T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
+        T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
+        T m = s[IM] + row[JM];
+        T x = s[IE] + row[J8_E2];
+        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
+        T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
+        const bool ok = nonzero3(rx, ry, rz);
+        InvR<T> w = soft_inv(x, ok);
+        // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv
+        T phi = m * w.r1;
+        T w2 = w.r2 * fma(T(2), phi, v2);
+        T gamma = w.r2 * fma(T(2) * w.r2, phi, w2);
+        gamma *= p.eta * rsqrt_masked(w2, ok);   // masked pair: seed 0 -> gamma 0 -> w2 stays 0
+        w2 = fma(-gamma, rv, w2);
+        a[0] += w2;
+        a[1] = rmax(w2, a[1]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA])
+    {
+        a[0] += b[0];
+        a[1] = rmax(a[1], b[1]);
+    }
+    static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params& p, T* const* out)
+    {
+        out[0][i] = p.eta * rsqrt_full(T(1) + a[0]);
+        out[1][i] = p.eta * rsqrt_full(T(1) + a[1]);
+    }
+};
+
+// =======================================================================================
+// nreg_X -- replaces nreg_Xkernel (nreg_kernels.c:5-65, core nreg_kernels_common.h:7-61);
+// 37 flop/pair.  Outputs: mrx mry mrz ax ay az u, with u = im * sum (nreg_kernels.c:63).
+// =======================================================================================
+template <typename T> struct DtParams { T dt; };
+template <typename T> struct NregXOp {
+    typedef T real;
+    typedef DtParams<T> Params;
+    enum { NI = 7, NJ = 8, NA = 7, NO = 7, WPT = 2, UNROLL = 4 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IX, IY, IZ, IE, IVX, IVY, IVZ };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
+        s[IVX] = a[5][i]; s[IVY] = a[6][i]; s[IVZ] = a[7][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row8(j, r, row); }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p)
+    {
+        T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
+        T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
+        rx = fma(vx, p.dt, rx); ry = fma(vy, p.dt, ry); rz = fma(vz, p.dt, rz);
+        T x = s[IE] + row[J8_E2];
+        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        T mj = row[JM];
+        T g = mj * w.r3;
+        a[0] = fma(mj, rx, a[0]); a[1] = fma(mj, ry, a[1]); a[2] = fma(mj, rz, a[2]);
+        a[3] = fma(-g, rx, a[3]); a[4] = fma(-g, ry, a[4]); a[5] = fma(-g, rz, a[5]);
+        a[6] = fma(mj, w.r1, a[6]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
+    static TUPAN_DEV void finish(const T* const* ia, long long i, const T (&a)[NA], const Params&, T* const* out)
+    {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out[k][i] = a[k];
+        out[6][i] = ia[0][i] * a[6];
+    }
+};
+
+// =======================================================================================
+// nreg_V -- replaces nreg_Vkernel (nreg_kernels.c:68-116, core nreg_kernels_common.h:63-102);
+// 25 flop/pair; no mask, no 1/r.  Caller arrays: m vx vy vz ax ay az.
+// Outputs: mvx mvy mvz mk with mk = im * sum (nreg_kernels.c:113).
+// =======================================================================================
+template <typename T> struct NregVOp {
+    typedef T real;
+    typedef DtParams<T> Params;
+    enum { NI = 6, NJ = 7, NA = 4, NO = 4, WPT = 4, UNROLL = 4 };
+    enum { NJP = round_up(NJ, Vec16<T>::N) };
+    enum { IVX, IVY, IVZ, IAX, IAY, IAZ };
+    enum { RV_VX = 0, RV_VY = 1, RV_VZ = 2, RV_M = 3, RV_AX = 4, RV_AY = 5, RV_AZ = 6 };
+    static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
+    {
+        s[IVX] = a[1][i]; s[IVY] = a[2][i]; s[IVZ] = a[3][i];
+        s[IAX] = a[4][i]; s[IAY] = a[5][i]; s[IAZ] = a[6][i];
+    }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP])
+    {
+        row[RV_M] = j[0][r];
+        row[RV_VX] = j[1][r]; row[RV_VY] = j[2][r]; row[RV_VZ] = j[3][r];
+        row[RV_AX] = j[4][r]; row[RV_AY] = j[5][r]; row[RV_AZ] = j[6][r];
+    }
+    static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
+    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p)
+    {
+        T vx = s[IVX] - row[RV_VX], vy = s[IVY] - row[RV_VY], vz = s[IVZ] - row[RV_VZ];
+        T ax = s[IAX] - row[RV_AX], ay = s[IAY] - row[RV_AY], az = s[IAZ] - row[RV_AZ];
+        vx = fma(ax, p.dt, vx); vy = fma(ay, p.dt, vy); vz = fma(az, p.dt, vz);
+        T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
+        T mj = row[RV_M];
+        a[0] = fma(mj, vx, a[0]); a[1] = fma(mj, vy, a[1]); a[2] = fma(mj, vz, a[2]);
+        a[3] = fma(mj, v2, a[3]);
+    }
+    static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
+    static TUPAN_DEV void finish(const T* const* ia, long long i, const T (&a)[NA], const Params&, T* const* out)
+    {
+        out[0][i] = a[0]; out[1][i] = a[1]; out[2][i] = a[2];
+        out[3][i] = ia[0][i] * a[3];
+    }
+};
+
+}  // namespace tupan

@@ -1,0 +1,358 @@
+// pair_engine.cuh -- the one O(ni*nj) engine every tupan pairwise kernel runs on.
+//
+// Shape of the problem (every kernel of tupan/lib/src is of this form, e.g. the double
+// loop acc_jerk_kernel.c:31-60):      out[i] = finish( reduce_j  pair(i, j) )
+//
+// B200 mapping
+//   * j-state: packed once per call by pack_j_kernel into rows of NJP reals (AoS, row =
+//     16-byte multiples) so that a tile of TJ rows is ONE contiguous block.  Tiles are
+//     streamed into shared memory by the TMA engine with 1-D bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) through a STAGES-deep ring of
+//     mbarrier-guarded buffers, issued by one elected thread; no thread spends registers
+//     or issue slots on staging.
+//   * i-state: WPT particles per thread, inputs and accumulators register-resident for the
+//     whole j sweep.  All lanes of a warp read the same packed row with 16-byte LDS
+//     (a broadcast, conflict-free).
+//   * small ni: JS = 2^k lanes of a warp share one i-particle and stride over the rows of a
+//     tile (lane split), partial accumulators are combined with warp shuffles; if that still
+//     leaves SMs idle, the j range is also split over blockIdx.y, raw accumulators go to a
+//     partial[slot][acc][i] workspace and finalize_kernel combines them and applies the
+//     kernel's epilogue (deterministic, no atomics).  The same workspace mechanism combines
+//     the local-shard and remote-shard sweeps of the multi-GPU path.
+//
+// An "Op" supplies the physics:
+//   typedef real;  enum { NI, NJ, NA, NO, WPT, UNROLL };  struct Params;
+//   load_i(const real* const* iarr, long long i, real (&s)[NI])
+//   pack_j(const real* const* jarr, long long j, real (&row)[NJP])
+//   zero(real (&a)[NA]);  pair(s, row, a, prm);  combine(a, b)
+//   finish(iarr, i, a, prm, real* const* out)
+#pragma once
+#include "common.cuh"
+
+namespace tupan {
+
+enum { MAX_IN = 14, MAX_OUT = 7 };
+
+template <typename T> struct InRefs  { const T* p[MAX_IN]; };
+template <typename T> struct OutRefs { T* p[MAX_OUT]; };
+
+template <class Op> struct Packed {
+    typedef typename Op::real T;
+    enum { NJP = round_up(Op::NJ, Vec16<T>::N), ROW_BYTES = NJP * sizeof(T) };
+};
+
+// ---------------------------------------------------------------------------------------
+// pack_j_kernel: SoA j arrays -> packed rows [j][NJP].  O(nj), coalesced reads.
+// ---------------------------------------------------------------------------------------
+template <class Op>
+__global__ void pack_j_kernel(InRefs<typename Op::real> j, long long nj, typename Op::real* __restrict__ packed)
+{
+    typedef typename Op::real T;
+    typedef typename Vec16<T>::type V;
+    constexpr int NJP = Packed<Op>::NJP;
+    constexpr int VN = Vec16<T>::N;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nj;
+         r += (long long)gridDim.x * blockDim.x) {
+        T row[NJP];
+#pragma unroll
+        for (int k = 0; k < NJP; ++k) row[k] = T(0);
+        Op::pack_j(j.p, r, row);
+        V* dst = reinterpret_cast<V*>(packed + r * NJP);
+#pragma unroll
+        for (int k = 0; k < NJP / VN; ++k) dst[k] = *reinterpret_cast<V*>(&row[k * VN]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// pair_kernel
+// ---------------------------------------------------------------------------------------
+template <class Op> struct PairArgs {
+    typedef typename Op::real T;
+    InRefs<T> i;            // caller's i arrays, libtupan.h order
+    long long ni;
+    const T* jpack;         // packed j rows
+    long long j0, j1;       // rows [j0, j1) are swept by this launch ...
+    long long jchunk;       // ... blockIdx.y takes rows [j0 + y*jchunk, +jchunk)
+    int js_log2;            // log2(lanes per i-particle), lane-split variant only
+    int slot0;              // first workspace slot of this launch
+    T* partial;             // nullptr: apply epilogue and write outputs directly
+    OutRefs<T> out;
+    typename Op::Params prm;
+};
+
+template <class Op, int TJ, int STAGES> struct PairSmem {
+    enum {
+        TILE_BYTES = TJ * Packed<Op>::ROW_BYTES,
+        BYTES = STAGES * TILE_BYTES + STAGES * 8
+    };
+};
+
+template <class Op>
+TUPAN_DEV void load_row(const typename Op::real* p, typename Op::real (&row)[Packed<Op>::NJP])
+{
+    typedef typename Op::real T;
+    typedef typename Vec16<T>::type V;
+    constexpr int VN = Vec16<T>::N;
+#pragma unroll
+    for (int k = 0; k < Packed<Op>::NJP / VN; ++k) {
+        V v = reinterpret_cast<const V*>(p)[k];
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int c = 0; c < VN; ++c) row[k * VN + c] = e[c];
+    }
+}
+
+template <class Op, int NT, int WPT, int TJ, int STAGES, bool LANE_SPLIT>
+__global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairArgs<Op> a)
+{
+    typedef typename Op::real T;
+    constexpr int NJP = Packed<Op>::NJP;
+    constexpr int TILE_ELEMS = TJ * NJP;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tiles = reinterpret_cast<T*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * TILE_ELEMS * sizeof(T));
+
+    const int tid = threadIdx.x;
+    const int jsl = LANE_SPLIT ? a.js_log2 : 0;
+    const int js = 1 << jsl;
+    const int jsub = tid & (js - 1);
+    const int islot = tid >> jsl;
+    const int slots = NT >> jsl;
+    const long long ibase = (long long)blockIdx.x * (slots * WPT);
+
+    T is[WPT][Op::NI];
+    T acc[WPT][Op::NA];
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) {
+        long long i = ibase + (long long)w * slots + islot;
+        if (i > a.ni - 1) i = a.ni - 1;  // clamp: computes a duplicate, never stored
+        Op::load_i(a.i.p, i, is[w]);
+        Op::zero(acc[w]);
+    }
+
+    const long long jlo = a.j0 + (long long)blockIdx.y * a.jchunk;
+    long long jhi = jlo + a.jchunk;
+    if (jhi > a.j1) jhi = a.j1;
+    const int ntiles = (jhi > jlo) ? (int)((jhi - jlo + TJ - 1) / TJ) : 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {  // elected thread: start the bulk copy of tile t
+        const int s = t % STAGES;
+        const long long r0 = jlo + (long long)t * TJ;
+        long long cnt = jhi - r0;
+        if (cnt > TJ) cnt = TJ;
+        const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(tiles + s * TILE_ELEMS, a.jpack + r0 * NJP, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < STAGES && t < ntiles; ++t) issue(t);
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
+        const T* sj = tiles + s * TILE_ELEMS;
+        long long rem = jhi - (jlo + (long long)t * TJ);
+        const int cnt = rem > TJ ? TJ : (int)rem;
+
+        if (!LANE_SPLIT) {
+            if (cnt == TJ) {
+#pragma unroll Op::UNROLL
+                for (int j = 0; j < TJ; ++j) {
+                    T row[NJP];
+                    load_row<Op>(sj + j * NJP, row);
+#pragma unroll
+                    for (int w = 0; w < WPT; ++w) Op::pair(is[w], row, acc[w], a.prm);
+                }
+            } else {
+                for (int j = 0; j < cnt; ++j) {
+                    T row[NJP];
+                    load_row<Op>(sj + j * NJP, row);
+#pragma unroll
+                    for (int w = 0; w < WPT; ++w) Op::pair(is[w], row, acc[w], a.prm);
+                }
+            }
+        } else {
+            for (int j = jsub; j < cnt; j += js) {
+                T row[NJP];
+                load_row<Op>(sj + j * NJP, row);
+#pragma unroll
+                for (int w = 0; w < WPT; ++w) Op::pair(is[w], row, acc[w], a.prm);
+            }
+        }
+        __syncthreads();  // every warp is done with stage s -> it may be refilled
+        if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+    }
+
+    if (LANE_SPLIT) {
+        for (int off = js >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) {
+                T other[Op::NA];
+#pragma unroll
+                for (int k = 0; k < Op::NA; ++k) other[k] = __shfl_xor_sync(0xffffffffu, acc[w][k], off);
+                Op::combine(acc[w], other);
+            }
+        }
+    }
+
+    if (jsub == 0) {
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+            const long long i = ibase + (long long)w * slots + islot;
+            if (i < a.ni) {
+                if (a.partial != nullptr) {
+                    T* dst = a.partial + ((long long)(a.slot0 + blockIdx.y) * Op::NA) * a.ni + i;
+#pragma unroll
+                    for (int k = 0; k < Op::NA; ++k) dst[(long long)k * a.ni] = acc[w][k];
+                } else {
+                    Op::finish(a.i.p, i, acc[w], a.prm, a.out.p);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize_kernel: combine nslots raw accumulator sets and apply the epilogue.
+// ---------------------------------------------------------------------------------------
+template <class Op>
+__global__ void finalize_kernel(InRefs<typename Op::real> iarr, long long ni,
+                                const typename Op::real* __restrict__ partial, int nslots,
+                                OutRefs<typename Op::real> out, typename Op::Params prm)
+{
+    typedef typename Op::real T;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= ni) return;
+    T acc[Op::NA];
+#pragma unroll
+    for (int k = 0; k < Op::NA; ++k) acc[k] = partial[(long long)k * ni + i];
+    for (int s = 1; s < nslots; ++s) {
+        T other[Op::NA];
+#pragma unroll
+        for (int k = 0; k < Op::NA; ++k) other[k] = partial[((long long)s * Op::NA + k) * ni + i];
+        Op::combine(acc, other);
+    }
+    Op::finish(iarr.p, i, acc, prm, out.p);
+}
+
+// ---------------------------------------------------------------------------------------
+// Host side: launch plan and launcher.
+// ---------------------------------------------------------------------------------------
+struct Plan {
+    int lane_split;  // 0: WPT particles per thread, lanes independent; 1: JS lanes per particle
+    int js_log2;     // lane-split only
+    int jg;          // number of j chunks over blockIdx.y (>1 -> workspace + finalize)
+};
+
+struct DeviceInfo {
+    int sm_count;
+};
+
+template <class Op> struct Tune {
+    enum { NT = 256, TJ = 128, STAGES = 4, NT_SPLIT = 128 };
+};
+
+template <class Op>
+inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
+{
+    Plan p = {0, 0, 1};
+    const long long resident = (long long)dev.sm_count * 512;  // threads we want in flight
+    const int TJ = Tune<Op>::TJ;
+    if ((ni + Op::WPT - 1) / Op::WPT >= resident) return p;     // big ni: throughput shape
+    p.lane_split = 1;
+    // lanes per particle: enough to fill the chip, never more than a tile can feed
+    while (p.js_log2 < 5 && (ni << p.js_log2) < resident && (TJ >> (p.js_log2 + 1)) >= 4) p.js_log2++;
+    long long threads = ni << p.js_log2;
+    long long want = (resident + threads - 1) / threads;        // j chunks to fill the rest
+    long long maxg = (nj + 4 * TJ - 1) / (4 * TJ);              // >= 4 tiles per chunk
+    if (want > maxg) want = maxg;
+    if (want > 64) want = 64;
+    if (want < 1) want = 1;
+    p.jg = (int)want;
+    return p;
+}
+
+// Sweep rows [j0, j1) of `jpack` for all ni particles.
+//   partial == nullptr (requires plan.jg == 1): epilogue applied, outputs written.
+//   partial != nullptr: raw accumulators go to slots [slot0, slot0 + plan.jg).
+template <class Op>
+inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real>& iarr, long long ni,
+                                const typename Op::real* jpack, long long j0, long long j1,
+                                const typename Op::Params& prm, typename Op::real* partial, int slot0,
+                                const OutRefs<typename Op::real>& out, cudaStream_t stream)
+{
+    typedef Tune<Op> U;
+    PairArgs<Op> a;
+    a.i = iarr;
+    a.ni = ni;
+    a.jpack = jpack;
+    a.j0 = j0;
+    a.j1 = j1;
+    const long long rows = j1 - j0;
+    long long chunk = (rows + plan.jg - 1) / plan.jg;
+    chunk = (chunk + U::TJ - 1) / U::TJ * U::TJ;
+    if (chunk < U::TJ) chunk = U::TJ;
+    a.jchunk = chunk;
+    a.js_log2 = plan.js_log2;
+    a.slot0 = slot0;
+    a.partial = partial;
+    a.out = out;
+    a.prm = prm;
+    if (ni <= 0) return cudaSuccess;
+    const size_t smem = PairSmem<Op, U::TJ, U::STAGES>::BYTES;
+    if (!plan.lane_split) {
+        auto k = pair_kernel<Op, U::NT, Op::WPT, U::TJ, U::STAGES, false>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        const long long per_cta = (long long)U::NT * Op::WPT;
+        dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
+        k<<<grid, U::NT, smem, stream>>>(a);
+    } else {
+        auto k = pair_kernel<Op, U::NT_SPLIT, 1, U::TJ, U::STAGES, true>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        const long long per_cta = (long long)(U::NT_SPLIT >> plan.js_log2);
+        dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
+        k<<<grid, U::NT_SPLIT, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <class Op>
+inline cudaError_t launch_pack(const InRefs<typename Op::real>& jarr, long long nj,
+                               typename Op::real* packed, cudaStream_t stream)
+{
+    if (nj <= 0) return cudaSuccess;
+    long long blocks = (nj + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_j_kernel<Op><<<(unsigned)blocks, 256, 0, stream>>>(jarr, nj, packed);
+    return cudaGetLastError();
+}
+
+template <class Op>
+inline cudaError_t launch_finalize(const InRefs<typename Op::real>& iarr, long long ni,
+                                   const typename Op::real* partial, int nslots,
+                                   const OutRefs<typename Op::real>& out, const typename Op::Params& prm,
+                                   cudaStream_t stream)
+{
+    if (ni <= 0) return cudaSuccess;
+    finalize_kernel<Op><<<(unsigned)((ni + 255) / 256), 256, 0, stream>>>(iarr, ni, partial, nslots, out, prm);
+    return cudaGetLastError();
+}
+
+}  // namespace tupan
