@@ -1,0 +1,206 @@
+/*
+ * libtupan_cuda.h -- C ABI of the B200-native tupan kernel libraries.
+ *
+ * Two shared objects with IDENTICAL symbol names, one per precision, exactly like the
+ * reference's cffi build (tupan/lib/cffi_backend.py:35-36,84-87):
+ *
+ *     libtupan_cuda_fp64.so   REAL = double, UINT = unsigned long, INT = long   (TUPAN_FP64)
+ *     libtupan_cuda_fp32.so   REAL = float,  UINT = unsigned int,  INT = int
+ *
+ * Part 1 is the drop-in: the ten entry points of tupan/lib/src/libtupan.h:2-246 with the
+ * same names, argument order and meaning -- `ni, <i arrays>, nj, <j arrays>, <scalars>,
+ * <output arrays>`, caller-owned HOST buffers of length >= ni / nj, outputs valid on
+ * return.  A maintainer can point tupan's cffi loader at these libraries unchanged (see
+ * INTEGRATION.md).  The i and j arrays may be the same arrays; kepler's outputs may alias
+ * its inputs (tupan/lib/extensions.py:642-646).
+ *
+ * Part 2 is what the reference has no equivalent of: device-resident entry points (device
+ * pointers + a CUDA stream, asynchronous), the building blocks of the multi-GPU path, and
+ * status / timing queries.  The reference's functions are `void` with no error channel
+ * (SURVEY.md 8b); Part-1 functions keep that signature, report failures on stderr and
+ * record them for tupan_cuda_last_error().
+ *
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef LIBTUPAN_CUDA_H
+#define LIBTUPAN_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef TUPAN_FP64
+typedef double REAL;
+typedef unsigned long UINT;
+typedef long INT;
+#else
+typedef float REAL;
+typedef unsigned int UINT;
+typedef int INT;
+#endif
+
+/* ------------------------------------------------------------------------------------ */
+/* Part 1 -- drop-in for tupan/lib/src/libtupan.h                                        */
+/* ------------------------------------------------------------------------------------ */
+
+/* replaces libtupan.h:2-15 (phi_kernel.c:5-35).  phi_i = -sum_j m_j / sqrt(r^2 + e2) */
+void phi_kernel(const UINT ni,
+                const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                const UINT nj,
+                const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                REAL *iphi);
+
+/* replaces libtupan.h:17-32 (acc_kernel.c:5-41) */
+void acc_kernel(const UINT ni,
+                const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                const UINT nj,
+                const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                REAL *iax, REAL *iay, REAL *iaz);
+
+/* replaces libtupan.h:34-58 (acc_jerk_kernel.c:5-61) -- the headline kernel */
+void acc_jerk_kernel(const UINT ni,
+                     const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                     const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                     const UINT nj,
+                     const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                     const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                     REAL *iax, REAL *iay, REAL *iaz, REAL *ijx, REAL *ijy, REAL *ijz);
+
+/* replaces libtupan.h:60-96 (snap_crackle_kernel.c:5-83) */
+void snap_crackle_kernel(const UINT ni,
+                         const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                         const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                         const REAL *iax, const REAL *iay, const REAL *iaz,
+                         const REAL *ijx, const REAL *ijy, const REAL *ijz,
+                         const UINT nj,
+                         const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                         const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                         const REAL *jax, const REAL *jay, const REAL *jaz,
+                         const REAL *jjx, const REAL *jjy, const REAL *jjz,
+                         REAL *isx, REAL *isy, REAL *isz, REAL *icx, REAL *icy, REAL *icz);
+
+/* replaces libtupan.h:98-119 (tstep_kernel.c:5-50).  idt_a = eta/sqrt(1+sum w2),
+ * idt_b = eta/sqrt(1+max w2) */
+void tstep_kernel(const UINT ni,
+                  const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                  const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                  const UINT nj,
+                  const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                  const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                  const REAL eta,
+                  REAL *idt_a, REAL *idt_b);
+
+/* replaces libtupan.h:121-150 (pnacc_kernel.c:5-61); inv_k = clight^-k */
+void pnacc_kernel(const UINT ni,
+                  const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                  const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                  const UINT nj,
+                  const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                  const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                  UINT order,
+                  const REAL inv1, const REAL inv2, const REAL inv3, const REAL inv4,
+                  const REAL inv5, const REAL inv6, const REAL inv7,
+                  REAL *ipnax, REAL *ipnay, REAL *ipnaz);
+
+/* replaces libtupan.h:152-178 (nreg_kernels.c:5-65) */
+void nreg_Xkernel(const UINT ni,
+                  const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                  const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                  const UINT nj,
+                  const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                  const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                  const REAL dt,
+                  REAL *idrx, REAL *idry, REAL *idrz, REAL *iax, REAL *iay, REAL *iaz, REAL *iu);
+
+/* replaces libtupan.h:180-201 (nreg_kernels.c:68-116) */
+void nreg_Vkernel(const UINT ni,
+                  const REAL *im, const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                  const REAL *iax, const REAL *iay, const REAL *iaz,
+                  const UINT nj,
+                  const REAL *jm, const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                  const REAL *jax, const REAL *jay, const REAL *jaz,
+                  const REAL dt,
+                  REAL *idvx, REAL *idvy, REAL *idvz, REAL *ik);
+
+/* replaces libtupan.h:203-229 (sakura_kernel.c:5-64); flag in {-2,-1,1,2}, else no-op */
+void sakura_kernel(const UINT ni,
+                   const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                   const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                   const UINT nj,
+                   const REAL *jm, const REAL *jrx, const REAL *jry, const REAL *jrz, const REAL *je2,
+                   const REAL *jvx, const REAL *jvy, const REAL *jvz,
+                   const REAL dt, const INT flag,
+                   REAL *idrx, REAL *idry, REAL *idrz, REAL *idvx, REAL *idvy, REAL *idvz);
+
+/* replaces libtupan.h:231-246 (kepler_solver_kernel.c:5-50); exactly two bodies */
+void kepler_solver_kernel(const REAL *im, const REAL *irx, const REAL *iry, const REAL *irz, const REAL *ie2,
+                          const REAL *ivx, const REAL *ivy, const REAL *ivz,
+                          const REAL dt,
+                          REAL *ir1x, REAL *ir1y, REAL *ir1z, REAL *iv1x, REAL *iv1y, REAL *iv1z);
+
+/* ------------------------------------------------------------------------------------ */
+/* Part 2 -- device-resident API, multi-GPU building blocks, status                       */
+/* ------------------------------------------------------------------------------------ */
+
+/* kernel ids for the generic entry points */
+enum tupan_kernel {
+    TUPAN_PHI = 0, TUPAN_ACC = 1, TUPAN_ACC_JERK = 2, TUPAN_SNAP_CRACKLE = 3, TUPAN_TSTEP = 4,
+    TUPAN_PNACC = 5, TUPAN_NREG_X = 6, TUPAN_NREG_V = 7, TUPAN_SAKURA = 8, TUPAN_KEPLER = 9
+};
+
+/* All functions below return 0 on success, non-zero on failure (see tupan_cuda_last_error).
+ * `iarr`/`jarr`/`out` are arrays of DEVICE pointers in the libtupan.h order of the kernel
+ * (e.g. acc_jerk: m rx ry rz e2 vx vy vz | ax ay az jx jy jz); `scal` holds the kernel's
+ * scalar arguments as doubles in libtupan.h order (tstep: eta; pnacc: order, inv1..inv7;
+ * nreg_X/V: dt; sakura: dt, flag; kepler: dt); `stream` is a cudaStream_t (NULL = legacy
+ * default stream).  Calls are asynchronous with respect to the host. */
+
+int tupan_cuda_info(int kernel, int *n_in, int *n_out, int *n_scal, int *flops_per_pair);
+
+/* out[i] = kernel(i-system, j-system): pack + sweep (+ finalize) on `stream` */
+int tupan_cuda_run_dev(int kernel, long long ni, const void *const *iarr, long long nj,
+                       const void *const *jarr, const double *scal, void *const *out, void *stream);
+
+/* kepler for `pairs` independent binaries: arrays hold 2*pairs bodies, binary b = (2b, 2b+1) */
+int tupan_cuda_kepler_dev(long long pairs, const void *const *arr, double dt, void *const *out, void *stream);
+
+/* Building blocks.  A packed j buffer has tupan_cuda_row_width(kernel) REALs per particle
+ * (row-major, 16-byte aligned rows) and can be all-gathered across GPUs as one tensor. */
+int tupan_cuda_row_width(int kernel, const double *scal);
+int tupan_cuda_n_acc(int kernel, const double *scal);
+int tupan_cuda_pack_dev(int kernel, long long nj, const void *const *jarr, const double *scal,
+                        void *packed, void *stream);
+/* number of workspace slots a sweep of `rows` rows for `ni` particles will write */
+int tupan_cuda_sweep_slots(int kernel, long long ni, long long rows, const double *scal);
+/* sweep packed rows [j0, j1) into raw accumulators partial[slot0 ...][n_acc][ni] */
+int tupan_cuda_sweep_dev(int kernel, long long ni, const void *const *iarr, const void *packed,
+                         long long j0, long long j1, const double *scal, void *partial, int slot0,
+                         void *stream);
+/* combine `nslots` accumulator sets, apply the kernel's epilogue, write outputs */
+int tupan_cuda_finalize_dev(int kernel, long long ni, const void *const *iarr, const void *partial,
+                            int nslots, const double *scal, void *const *out, void *stream);
+
+/* min over i of |tstep[i]| on the device (the host-side reduction of
+ * tupan/particles/body.py:364-368 fused behind tstep); result is written to *d_min. */
+int tupan_cuda_abs_min_dev(long long n, const void *d_values, void *d_min, void *stream);
+
+/* status, tuning, measurement */
+int tupan_cuda_init(void);                         /* create the context on the current device */
+int tupan_cuda_last_error(char *msg, int msg_len); /* code of the last failure (0 = none) */
+void tupan_cuda_clear_error(void);
+/* force a launch shape (tests/tuning): lane_split < 0 restores the heuristic */
+void tupan_cuda_force_plan(int lane_split, int js_log2, int jg);
+void tupan_cuda_last_plan(int *lane_split, int *js_log2, int *jg);
+void tupan_cuda_set_timing(int enable);
+/* stage times of the last Part-1 call, milliseconds (CUDA events on the library stream) */
+void tupan_cuda_last_times(float *h2d, float *pack, float *pair, float *finalize, float *d2h);
+long long tupan_cuda_launch_count(void);           /* kernels launched since load */
+int tupan_cuda_sm_count(void);
+/* FMA-pipe micro-benchmark in the library's precision: sustained TFLOP/s over `ms` ms */
+int tupan_cuda_fma_peak(double ms, double *tflops, double *sm_mhz_effective);
+int tupan_cuda_real_bytes(void);                   /* sizeof(REAL): 8 or 4 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBTUPAN_CUDA_H */

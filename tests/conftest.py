@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_oracle():
+    """The CPU oracle is test infrastructure; make sure it is compiled (seconds)."""
+    import oracle
+    if not (oracle.have("oracle", "float64") and oracle.have("oracle", "float32")):
+        oracle.build()
+    yield

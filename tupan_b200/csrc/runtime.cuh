@@ -1,0 +1,267 @@
+// runtime.cuh -- host-side runtime shared by every kernel family: the per-library context
+// (stream, cached device buffers, timing events, error state) and the generic runners that
+// turn an Op into the entry points of a KernelVTable.
+#pragma once
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+#include "pair_engine.cuh"
+
+namespace tupan {
+
+enum KernelId {
+    K_PHI = 0, K_ACC, K_ACC_JERK, K_SNAP_CRACKLE, K_TSTEP, K_PNACC, K_NREG_X, K_NREG_V, K_SAKURA,
+    K_KEPLER, K_COUNT
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes);
+    void release();
+};
+
+struct StageTimes { float h2d_ms, pack_ms, pair_ms, finalize_ms, d2h_ms; };
+
+struct Context {
+    std::mutex mu;
+    bool ready = false;
+    int device = -1;
+    DeviceInfo info = {148};
+    cudaStream_t stream = nullptr;
+    DevBuf in_i[MAX_IN], in_j[MAX_IN], outb[MAX_OUT], jpack, partial;
+    // forced launch plan (tests, tuning); lane_split < 0 means "choose"
+    Plan forced = {-1, 0, 1};
+    // timing of the last call (only when enabled)
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    StageTimes last = {0, 0, 0, 0, 0};
+    Plan last_plan = {0, 0, 1};
+    long long launches = 0;   // kernels launched by this library since load
+    int last_error = 0;       // 0 = ok, else cudaError_t (or -1 for argument errors)
+    char last_msg[256] = {0};
+
+    int init();
+    int fail(cudaError_t e, const char* where);
+    void mark(int k, cudaStream_t s) { if (timing) cudaEventRecord(ev[k], s); }
+};
+
+Context& ctx();
+
+#define TUPAN_CHECK(call, where)                               \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return ctx().fail(e__, where); \
+    } while (0)
+
+// What every kernel family exports to the ABI layer.  `scal` carries the kernel's scalar
+// arguments as doubles in libtupan.h order (eta | order,inv1..inv7 | dt | dt,flag).
+struct KernelVTable {
+    const char* name;
+    int n_in;        // caller arrays per side
+    int n_out;       // output arrays
+    int n_scal;      // scalars in `scal`
+    int flops;       // reference flops/pair convention (0 = data dependent)
+    int (*row_width)(const double* scal);  // reals per packed row
+    int (*n_acc)(const double* scal);      // raw accumulators per particle
+    // host pointers in, host pointers out, synchronous (the libtupan.h contract)
+    int (*run_host)(long long ni, const real_t* const* hi, long long nj, const real_t* const* hj,
+                    const double* scal, real_t* const* hout);
+    // device pointers, asynchronous on `stream`
+    int (*run_dev)(long long ni, const real_t* const* di, long long nj, const real_t* const* dj,
+                   const double* scal, real_t* const* dout, cudaStream_t stream);
+    // building blocks (device-resident / multi-GPU path)
+    int (*pack)(long long nj, const real_t* const* dj, const double* scal, real_t* packed, cudaStream_t stream);
+    int (*sweep_slots)(long long ni, long long rows, const double* scal);
+    int (*sweep)(long long ni, const real_t* const* di, const real_t* packed, long long j0, long long j1,
+                 const double* scal, real_t* partial, int slot0, cudaStream_t stream);
+    int (*finalize)(long long ni, const real_t* const* di, const real_t* partial, int nslots,
+                    const double* scal, real_t* const* dout, cudaStream_t stream);
+};
+
+const KernelVTable* vtable(int kernel);
+
+// ---------------------------------------------------------------------------------------
+// Generic runners
+// ---------------------------------------------------------------------------------------
+template <class Op> struct Runner {
+    typedef typename Op::real T;
+    enum { NJP = Packed<Op>::NJP };
+
+    static InRefs<T> in_refs(const T* const* a, int n)
+    {
+        InRefs<T> r;
+        for (int k = 0; k < MAX_IN; ++k) r.p[k] = k < n ? a[k] : nullptr;
+        return r;
+    }
+    static OutRefs<T> out_refs(T* const* a, int n)
+    {
+        OutRefs<T> r;
+        for (int k = 0; k < MAX_OUT; ++k) r.p[k] = k < n ? a[k] : nullptr;
+        return r;
+    }
+    static Plan plan_for(long long ni, long long rows)
+    {
+        Context& c = ctx();
+        Plan p = c.forced.lane_split >= 0 ? c.forced : choose_plan<Op>(c.info, ni, rows);
+        if (p.jg < 1) p.jg = 1;
+        if (p.js_log2 < 0) p.js_log2 = 0;
+        if (p.js_log2 > 5) p.js_log2 = 5;
+        if (!p.lane_split) p.js_log2 = 0;
+        return p;
+    }
+
+    static int row_width(const double*) { return NJP; }
+    static int n_acc(const double*) { return Op::NA; }
+
+    static int pack(int n_in, long long nj, const T* const* dj, T* packed, cudaStream_t s)
+    {
+        TUPAN_CHECK(launch_pack<Op>(in_refs(dj, n_in), nj, packed, s), "pack_j");
+        if (nj > 0) ctx().launches++;
+        return 0;
+    }
+    static int sweep_slots(long long ni, long long rows) { return plan_for(ni, rows).jg; }
+    static int sweep(int n_in, long long ni, const T* const* di, const T* packed, long long j0, long long j1,
+                     const typename Op::Params& prm, T* partial, int slot0, cudaStream_t s)
+    {
+        Plan p = plan_for(ni, j1 - j0);
+        OutRefs<T> none = out_refs(nullptr, 0);
+        TUPAN_CHECK(launch_pairs<Op>(p, in_refs(di, n_in), ni, packed, j0, j1, prm, partial, slot0, none, s),
+                    "pair sweep");
+        if (ni > 0) ctx().launches++;
+        ctx().last_plan = p;
+        return 0;
+    }
+    static int finalize(int n_in, int n_out, long long ni, const T* const* di, const T* partial, int nslots,
+                        const typename Op::Params& prm, T* const* dout, cudaStream_t s)
+    {
+        TUPAN_CHECK(launch_finalize<Op>(in_refs(di, n_in), ni, partial, nslots, out_refs(dout, n_out), prm, s),
+                    "finalize");
+        if (ni > 0) ctx().launches++;
+        return 0;
+    }
+
+    // device pointers in/out; uses the context's packed/partial buffers
+    static int run_dev(int n_in, int n_out, long long ni, const T* const* di, long long nj, const T* const* dj,
+                       const typename Op::Params& prm, T* const* dout, cudaStream_t s)
+    {
+        Context& c = ctx();
+        if (ni <= 0) return 0;
+        T* packed = static_cast<T*>(c.jpack.ensure((size_t)(nj > 0 ? nj : 1) * NJP * sizeof(T)));
+        if (!packed) return c.fail(cudaErrorMemoryAllocation, "packed j buffer");
+        c.mark(1, s);
+        int rc = pack(n_in, nj, dj, packed, s);
+        if (rc) return rc;
+        c.mark(2, s);
+        Plan p = plan_for(ni, nj);
+        c.last_plan = p;
+        if (p.jg == 1) {
+            TUPAN_CHECK(launch_pairs<Op>(p, in_refs(di, n_in), ni, packed, 0, nj, prm, nullptr, 0,
+                                         out_refs(dout, n_out), s),
+                        "pair kernel");
+            c.launches++;
+            c.mark(3, s);
+        } else {
+            T* part = static_cast<T*>(c.partial.ensure((size_t)p.jg * Op::NA * ni * sizeof(T)));
+            if (!part) return c.fail(cudaErrorMemoryAllocation, "partial workspace");
+            OutRefs<T> none = out_refs(nullptr, 0);
+            TUPAN_CHECK(launch_pairs<Op>(p, in_refs(di, n_in), ni, packed, 0, nj, prm, part, 0, none, s),
+                        "pair kernel");
+            c.launches++;
+            c.mark(3, s);
+            rc = finalize(n_in, n_out, ni, di, part, p.jg, prm, dout, s);
+            if (rc) return rc;
+        }
+        c.mark(4, s);
+        return 0;
+    }
+
+    // host pointers in/out (libtupan.h contract): H2D, run, D2H, synchronous return.
+    // A j array that is the same host array as an i array (ips is jps, or a prefix slice of
+    // it) is not copied twice.
+    static int run_host(int n_in, int n_out, long long ni, const T* const* hi, long long nj, const T* const* hj,
+                        const typename Op::Params& prm, T* const* hout)
+    {
+        Context& c = ctx();
+        std::lock_guard<std::mutex> lock(c.mu);
+        int rc = c.init();
+        if (rc) return rc;
+        if (ni <= 0) return 0;
+        cudaStream_t s = c.stream;
+        const T* di[MAX_IN];
+        const T* dj[MAX_IN];
+        T* dout[MAX_OUT];
+        c.mark(0, s);
+        for (int k = 0; k < n_in; ++k) {
+            T* d = static_cast<T*>(c.in_i[k].ensure((size_t)ni * sizeof(T)));
+            if (!d) return c.fail(cudaErrorMemoryAllocation, "i buffer");
+            TUPAN_CHECK(cudaMemcpyAsync(d, hi[k], (size_t)ni * sizeof(T), cudaMemcpyHostToDevice, s), "H2D i");
+            di[k] = d;
+        }
+        for (int k = 0; k < n_in; ++k) {
+            dj[k] = nullptr;
+            if (nj <= ni) {
+                for (int q = 0; q < n_in; ++q)
+                    if (hj[k] == hi[q]) { dj[k] = di[q]; break; }
+            }
+            if (!dj[k] && nj > 0) {
+                T* d = static_cast<T*>(c.in_j[k].ensure((size_t)nj * sizeof(T)));
+                if (!d) return c.fail(cudaErrorMemoryAllocation, "j buffer");
+                TUPAN_CHECK(cudaMemcpyAsync(d, hj[k], (size_t)nj * sizeof(T), cudaMemcpyHostToDevice, s), "H2D j");
+                dj[k] = d;
+            }
+        }
+        for (int k = 0; k < n_out; ++k) {
+            dout[k] = static_cast<T*>(c.outb[k].ensure((size_t)ni * sizeof(T)));
+            if (!dout[k]) return c.fail(cudaErrorMemoryAllocation, "out buffer");
+        }
+        rc = run_dev(n_in, n_out, ni, di, nj, dj, prm, dout, s);
+        if (rc) return rc;
+        for (int k = 0; k < n_out; ++k)
+            TUPAN_CHECK(cudaMemcpyAsync(hout[k], dout[k], (size_t)ni * sizeof(T), cudaMemcpyDeviceToHost, s), "D2H");
+        c.mark(5, s);
+        TUPAN_CHECK(cudaStreamSynchronize(s), "synchronize");
+        if (c.timing) {
+            cudaEventElapsedTime(&c.last.h2d_ms, c.ev[0], c.ev[1]);
+            cudaEventElapsedTime(&c.last.pack_ms, c.ev[1], c.ev[2]);
+            cudaEventElapsedTime(&c.last.pair_ms, c.ev[2], c.ev[3]);
+            cudaEventElapsedTime(&c.last.finalize_ms, c.ev[3], c.ev[4]);
+            cudaEventElapsedTime(&c.last.d2h_ms, c.ev[4], c.ev[5]);
+        }
+        return 0;
+    }
+};
+
+// Glue: build the vtable entry points of an Op whose Params come from `scal` via MakePrm.
+#define TUPAN_DEFINE_VTABLE(VT, OP, NAME, N_IN, N_OUT, N_SCAL, FLOPS, MAKEPRM)                                   \
+    namespace {                                                                                                   \
+    typedef Runner<OP> R_##VT;                                                                                    \
+    int VT##_rw(const double* s) { return R_##VT::row_width(s); }                                                 \
+    int VT##_na(const double* s) { return R_##VT::n_acc(s); }                                                     \
+    int VT##_host(long long ni, const real_t* const* hi, long long nj, const real_t* const* hj,                  \
+                  const double* s, real_t* const* ho)                                                             \
+    { return R_##VT::run_host(N_IN, N_OUT, ni, hi, nj, hj, MAKEPRM(s), ho); }                                     \
+    int VT##_dev(long long ni, const real_t* const* di, long long nj, const real_t* const* dj, const double* s,   \
+                 real_t* const* dout, cudaStream_t st)                                                            \
+    {                                                                                                             \
+        Context& c = ctx();                                                                                       \
+        std::lock_guard<std::mutex> lock(c.mu);                                                                   \
+        int rc = c.init();                                                                                        \
+        if (rc) return rc;                                                                                        \
+        return R_##VT::run_dev(N_IN, N_OUT, ni, di, nj, dj, MAKEPRM(s), dout, st);                                \
+    }                                                                                                             \
+    int VT##_pack(long long nj, const real_t* const* dj, const double*, real_t* packed, cudaStream_t st)         \
+    { return R_##VT::pack(N_IN, nj, dj, packed, st); }                                                            \
+    int VT##_slots(long long ni, long long rows, const double*) { return R_##VT::sweep_slots(ni, rows); }        \
+    int VT##_sweep(long long ni, const real_t* const* di, const real_t* packed, long long j0, long long j1,      \
+                   const double* s, real_t* partial, int slot0, cudaStream_t st)                                  \
+    { return R_##VT::sweep(N_IN, ni, di, packed, j0, j1, MAKEPRM(s), partial, slot0, st); }                       \
+    int VT##_fin(long long ni, const real_t* const* di, const real_t* partial, int nslots, const double* s,      \
+                 real_t* const* dout, cudaStream_t st)                                                            \
+    { return R_##VT::finalize(N_IN, N_OUT, ni, di, partial, nslots, MAKEPRM(s), dout, st); }                      \
+    }                                                                                                             \
+    extern const KernelVTable VT = {NAME,      N_IN,      N_OUT,     N_SCAL,     FLOPS,      VT##_rw,  VT##_na,   \
+                                    VT##_host, VT##_dev,  VT##_pack, VT##_slots, VT##_sweep, VT##_fin};
+
+}  // namespace tupan
