@@ -192,7 +192,8 @@ void tupan_cuda_clear_error(void);
 void tupan_cuda_force_plan(int lane_split, int js_log2, int jg);
 void tupan_cuda_last_plan(int *lane_split, int *js_log2, int *jg);
 void tupan_cuda_set_timing(int enable);
-/* stage times of the last Part-1 call, milliseconds (CUDA events on the library stream) */
+/* stage times of the last call, milliseconds (CUDA events on the stream the call ran on;
+ * a device-resident call has no h2d/d2h stage and reports 0 for them) */
 void tupan_cuda_last_times(float *h2d, float *pack, float *pair, float *finalize, float *d2h);
 long long tupan_cuda_launch_count(void);           /* kernels launched since load */
 int tupan_cuda_sm_count(void);

@@ -276,6 +276,13 @@ void tupan_cuda_set_timing(int enable) { ctx().timing = enable != 0; }
 void tupan_cuda_last_times(float* h2d, float* pack, float* pair, float* fin, float* d2h)
 {
     Context& c = ctx();
+    // stage k lies between ev[k] and ev[k+1]; a device-resident call records ev[1..4] only
+    float* dst[5] = {&c.last.h2d_ms, &c.last.pack_ms, &c.last.pair_ms, &c.last.finalize_ms, &c.last.d2h_ms};
+    for (int k = 0; k < 5; ++k) {
+        *dst[k] = 0;
+        if ((c.marked >> k & 1u) && (c.marked >> (k + 1) & 1u) && cudaEventSynchronize(c.ev[k + 1]) == cudaSuccess)
+            cudaEventElapsedTime(dst[k], c.ev[k], c.ev[k + 1]);
+    }
     if (h2d) *h2d = c.last.h2d_ms;
     if (pack) *pack = c.last.pack_ms;
     if (pair) *pair = c.last.pair_ms;

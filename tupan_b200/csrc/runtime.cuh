@@ -44,7 +44,15 @@ struct Context {
 
     int init();
     int fail(cudaError_t e, const char* where);
-    void mark(int k, cudaStream_t s) { if (timing) cudaEventRecord(ev[k], s); }
+    unsigned marked = 0;      // which of ev[] were recorded by the last call
+    void mark(int k, cudaStream_t s)
+    {
+        if (!timing) return;
+        // a new call starts at ev[0] (host-pointer entry) or at ev[1] (device-resident entry)
+        if (k == 0 || (k == 1 && marked != 1u)) marked = 0;
+        cudaEventRecord(ev[k], s);
+        marked |= 1u << k;
+    }
 };
 
 Context& ctx();
@@ -222,13 +230,6 @@ template <class Op> struct Runner {
             TUPAN_CHECK(cudaMemcpyAsync(hout[k], dout[k], (size_t)ni * sizeof(T), cudaMemcpyDeviceToHost, s), "D2H");
         c.mark(5, s);
         TUPAN_CHECK(cudaStreamSynchronize(s), "synchronize");
-        if (c.timing) {
-            cudaEventElapsedTime(&c.last.h2d_ms, c.ev[0], c.ev[1]);
-            cudaEventElapsedTime(&c.last.pack_ms, c.ev[1], c.ev[2]);
-            cudaEventElapsedTime(&c.last.pair_ms, c.ev[2], c.ev[3]);
-            cudaEventElapsedTime(&c.last.finalize_ms, c.ev[3], c.ev[4]);
-            cudaEventElapsedTime(&c.last.d2h_ms, c.ev[4], c.ev[5]);
-        }
         return 0;
     }
 };
