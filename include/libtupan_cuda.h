@@ -164,6 +164,13 @@ int tupan_cuda_run_dev(int kernel, long long ni, const void *const *iarr, long l
 /* kepler for `pairs` independent binaries: arrays hold 2*pairs bodies, binary b = (2b, 2b+1) */
 int tupan_cuda_kepler_dev(long long pairs, const void *const *arr, double dt, void *const *out, void *stream);
 
+/* The Kepler propagator inside sakura / kepler bounds its sub-step doubling at 2^16 (the
+ * reference, universal_kepler_solver.h:481-606, doubles without bound: minutes on a host
+ * core for softened tight binaries).  The synchronous Part-1 entry points fail loudly when a
+ * pair hits the bound; after asynchronous *_dev calls query it here: returns the number of
+ * such pairs since the last query and resets it (synchronises the device); < 0 on error. */
+long long tupan_cuda_kepler_limit_hits(void);
+
 /* Building blocks.  A packed j buffer has tupan_cuda_row_width(kernel) REALs per particle
  * (row-major, 16-byte aligned rows) and can be all-gathered across GPUs as one tensor. */
 int tupan_cuda_row_width(int kernel, const double *scal);

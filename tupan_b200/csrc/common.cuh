@@ -33,70 +33,104 @@ template <> struct Vec16<float>  { enum { N = 4 }; typedef float4 type; };
 constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------
-// Zero test of the separation vector.  The reference masks a pair when r2 > 0 is false
-// (e.g. acc_jerk_kernel_common.h:36).  We test the separation itself -- for doubles with
-// integer ops, so the test stays off the FP64 pipe -- and additionally treat a pair whose
-// softened r2+e2 is not a positive normal number (rsqrt seed = inf) as masked.  The two
-// definitions differ only when r2 underflows to zero for a non-zero separation.
-// ---------------------------------------------------------------------------------------
-TUPAN_DEV bool nonzero3(double x, double y, double z)
-{
-    unsigned lo = (unsigned)__double2loint(x) | (unsigned)__double2loint(y) | (unsigned)__double2loint(z);
-    unsigned hi = (unsigned)__double2hiint(x) | (unsigned)__double2hiint(y) | (unsigned)__double2hiint(z);
-    return ((hi & 0x7fffffffu) | lo) != 0u;
-}
-TUPAN_DEV bool nonzero3(float x, float y, float z)
-{
-    return (x != 0.0f) | (y != 0.0f) | (z != 0.0f);
-}
-
-// ---------------------------------------------------------------------------------------
 // Masked reciprocal square root.
 //
-// fp64: MUFU.RSQ64H seed (PTX rsqrt.approx.ftz.f64, ~20 bits, looks at the high word only,
-// so it costs no FP64-pipe slot and no conversion) followed by ONE third-order step
-//     h = 1 - x*y0^2 ,  y = y0 + y0*h*(1/2 + 3/8 h)            (error ~ 5/16 h^3 < 2^-58)
-// = 5 FP64 instructions (DMUL, DFMA, DFMA, DMUL, DFMA).  The mask is applied to the SEED
-// with an integer select: a zero seed stays exactly zero through the refinement, so a
-// masked pair contributes exact zeros and no 0*inf is ever formed (the reference selects
-// after the divide instead, smoothing.h:140-143).
+// The reference masks a pair when `r2 > 0` is false (e.g. acc_jerk_kernel_common.h:36) and
+// forces inv_r2 = 0 after the divide (smoothing.h:140-143).  Here r2 = rx^2+ry^2+rz^2 is kept
+// separate from the softened x = r2 + e2 and the mask is read off r2 itself.
 //
-// fp32: MUFU.RSQ (rsqrt.approx.ftz.f32, max rel. error 2^-22.4) and a select.
+// What shapes this code (measured on B200, tools/microbench.cu + tools/kernel_lab.cu):
+//   * the FP64 pipe takes one warp instruction per 2 cycles per SM sub-partition, and every
+//     OTHER instruction issued costs about one more cycle -- integer mask arithmetic is not
+//     free in the shadow of the FP64 pipe.  Testing the six words of (rx, ry, rz) cost 7
+//     integer instructions per pair; the exponent test of r2 costs 2 (ISETP + SEL);
+//   * a DFMA with three distinct register operands takes 3 cycles (64-bit operands, two
+//     register banks), with two it takes 2: the refinement below has none with three.
+//
+// fp64: MUFU.RSQ64H seed (PTX rsqrt.approx.ftz.f64; measured max rel. error 2^-20.06; reads
+// the high word only) and ONE third-order step
+//     h = 1 - x*y0^2 ,  y = y0 * (k0 + h*(k1 + k2*h)),   (k0,k1,k2) = k*(1, 1/2, 3/8)
+// = 5 FP64 instructions (DMUL, DFMA, DFMA, DFMA, DMUL) returning k/sqrt(x) -- a constant
+// factor k rides along for free (acc_jerk uses k = sqrt 3).  Remaining error ~ 5/16 h^3 < 2^-58.
+// The mask zeroes the seed's HIGH word with an integer select: r2 < 2^-1022 (zero or
+// denormal, where the reference's r2 > 0 divide would overflow anyway) -> seed ~ 0 -> every
+// product downstream is exactly 0, no 0*inf is ever formed.  x <= 0 implies r2 fails the test
+// as long as e2 >= 0, so the seed is never inf/NaN for an unmasked pair.
+//   CLEAN = true : the seed's low word is zeroed too (one more MOV): masked r1 is exactly 0.
+//   CLEAN = false: the low word keeps the raw MUFU bits (perturbs an unmasked seed by < 2^-20,
+//                  absorbed by the cubic step); a masked r1 is a denormal ~1e-314 whose square
+//                  underflows to exactly 0 -- for kernels that use r1 only through r1^2, r1^3.
+//
+// fp32: MUFU.RSQ (rsqrt.approx.ftz.f32, max rel. error 2^-22.4), select on r2 > 0, one Newton
+// step  y = y0 * (k0 + k1*h).
 // ---------------------------------------------------------------------------------------
-TUPAN_DEV double rsqrt_masked(double x, bool ok)
+template <bool CLEAN>
+TUPAN_DEV double rsqrt_seed_masked(double x, double r2)
 {
     double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    int hi = __double2hiint(y0);
-    ok = ok && (hi != 0x7ff00000);
-    y0 = __hiloint2double(ok ? hi : 0, 0);
-    double t = x * y0;
-    double h = fma(-t, y0, 1.0);
-    double p = fma(h, 0.375, 0.5);
-    double q = y0 * h;
-    return fma(q, p, y0);
+    if (CLEAN) {
+        asm("{\n"
+            ".reg .pred p;\n"
+            ".reg .f64 y;\n"
+            ".reg .b32 lo, hi, yl, yh;\n"
+            "mov.b64 {lo, hi}, %2;\n"
+            "setp.ge.u32 p, hi, 0x00100000;\n"
+            "rsqrt.approx.ftz.f64 y, %1;\n"
+            "mov.b64 {yl, yh}, y;\n"
+            "selp.b32 yh, yh, 0, p;\n"
+            "mov.b64 %0, {0, yh};\n"
+            "}\n"
+            : "=d"(y0)
+            : "d"(x), "d"(r2));
+    } else {
+        asm("{\n"
+            ".reg .pred p;\n"
+            ".reg .f64 y;\n"
+            ".reg .b32 lo, hi, yl, yh, ys;\n"
+            "mov.b64 {lo, hi}, %2;\n"
+            "setp.ge.u32 p, hi, 0x00100000;\n"
+            "rsqrt.approx.ftz.f64 y, %1;\n"
+            "mov.b64 {yl, yh}, y;\n"
+            "selp.b32 ys, yh, 0, p;\n"
+            "mov.b64 %0, {yh, ys};\n"
+            "}\n"
+            : "=d"(y0)
+            : "d"(x), "d"(r2));
+    }
+    return y0;
 }
-TUPAN_DEV float rsqrt_masked(float x, bool ok)
+
+// k/sqrt(x), masked by r2 (see above).  k0 = k, k1 = k/2, k2 = 3k/8.
+template <bool CLEAN>
+TUPAN_DEV double rsqrt_scaled(double x, double r2, double k0, double k1, double k2)
+{
+    const double y0 = rsqrt_seed_masked<CLEAN>(x, r2);
+    const double t = x * y0;
+    const double h = fma(-t, y0, 1.0);
+    const double p = fma(h, k2, k1);
+    const double c = fma(h, p, k0);
+    return y0 * c;
+}
+template <bool CLEAN>
+TUPAN_DEV float rsqrt_scaled(float x, float r2, float k0, float k1, float)
 {
     float y0;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
-    ok = ok && (x > 0.0f);
-    // one Newton step: keeps fp32 results as close to the correctly rounded reference
-    // chain (1/x, sqrt, *) as the accumulation order allows
-    y0 = ok ? y0 : 0.0f;
-    float h = fmaf(-x * y0, y0, 1.0f);
-    return fmaf(0.5f * y0, h, y0);
+    y0 = (r2 > 0.0f) ? y0 : 0.0f;
+    const float h = fmaf(-x * y0, y0, 1.0f);
+    return y0 * fmaf(h, k1, k0);
 }
 
 template <typename T> struct InvR { T r1, r2, r3; };
 
-// x = r2 + e2 (softened), ok = pair not masked.  Returns 1/r, 1/r^2, 1/r^3 (all exactly 0
-// when masked).  Unused members are dead-code-eliminated.
-template <typename T>
-TUPAN_DEV InvR<T> soft_inv(T x, bool ok)
+// x = r2 + e2 (softened).  Returns 1/r, 1/r^2, 1/r^3 of the softened distance, all 0 when the
+// pair is masked (CLEAN = false: r1 is a denormal instead, see above).  Unused members are
+// dead-code-eliminated.
+template <bool CLEAN, typename T>
+TUPAN_DEV InvR<T> soft_inv(T x, T r2)
 {
     InvR<T> o;
-    o.r1 = rsqrt_masked(x, ok);
+    o.r1 = rsqrt_scaled<CLEAN>(x, r2, T(1), T(0.5), T(0.375));
     o.r2 = o.r1 * o.r1;
     o.r3 = o.r2 * o.r1;
     return o;

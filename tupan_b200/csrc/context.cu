@@ -83,6 +83,7 @@ const KernelVTable* vtable(int kernel)
 }
 
 int kepler_run_dev(long long pairs, const real_t* const* din, double dt, real_t* const* dout, cudaStream_t st);
+long long kepler_limit_take();
 
 // ---- |x| minimum (fused tstep follow-up) ------------------------------------------------
 __global__ void abs_min_kernel(const real_t* __restrict__ v, long long n, real_t* __restrict__ out)
@@ -168,6 +169,14 @@ int tupan_cuda_kepler_dev(long long pairs, const void* const* arr, double dt, vo
     int rc = c.init();
     if (rc) return rc;
     return kepler_run_dev(pairs, (const real_t* const*)arr, dt, (real_t* const*)out, (cudaStream_t)stream);
+}
+
+long long tupan_cuda_kepler_limit_hits(void)
+{
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.init()) return -1;
+    return kepler_limit_take();
 }
 
 int tupan_cuda_row_width(int kernel, const double* scal)

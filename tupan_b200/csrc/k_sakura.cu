@@ -11,7 +11,43 @@ static inline SakuraParams<real_t> sakura_params(const double* s)
     p.flag = (int)s[1];
     return p;
 }
-TUPAN_DEFINE_VTABLE(vt_sakura, SakuraOp<real_t>, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+TUPAN_DEFINE_VTABLE(vt_sakura_raw, SakuraOp<real_t>, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+
+// Read and reset the count of pairs whose Kepler sub-stepping hit the 2^MAX_DOUBLINGS bound
+// (synchronises the device).  < 0 on a CUDA error.
+long long kepler_limit_take()
+{
+    unsigned int hits = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&hits, kepler_limit_hits, sizeof(hits)) != cudaSuccess) return -1;
+    if (hits != 0 && cudaMemcpyToSymbol(kepler_limit_hits, &zero, sizeof(zero)) != cudaSuccess) return -1;
+    return (long long)hits;
+}
+static int kepler_limit_check(const char* where)
+{
+    const long long hits = kepler_limit_take();
+    if (hits == 0) return 0;
+    Context& c = ctx();
+    c.last_error = hits < 0 ? (int)cudaGetLastError() : -2;
+    snprintf(c.last_msg, sizeof(c.last_msg),
+             "tupan_cuda: %s: %lld pair(s) needed more than 2^%d Kepler sub-steps (softened tight binary); "
+             "result not converged", where, hits, (int)MAX_DOUBLINGS);
+    fprintf(stderr, "%s\n", c.last_msg);
+    return c.last_error;
+}
+
+// sakura: the pair engine entry points, plus the sub-step-limit check on the synchronous path
+namespace {
+int sakura_host(long long ni, const real_t* const* hi, long long nj, const real_t* const* hj, const double* s,
+                real_t* const* ho)
+{
+    int rc = vt_sakura_raw.run_host(ni, hi, nj, hj, s, ho);
+    if (rc) return rc;
+    return kepler_limit_check("sakura_kernel");
+}
+}  // namespace
+extern const KernelVTable vt_sakura = {"sakura_kernel", 8, 6, 2, 0, vt_sakura_raw.row_width, vt_sakura_raw.n_acc,
+                                       sakura_host, vt_sakura_raw.run_dev, vt_sakura_raw.pack,
+                                       vt_sakura_raw.sweep_slots, vt_sakura_raw.sweep, vt_sakura_raw.finalize};
 
 // kepler_solver_kernel: arrays of 2*pairs bodies; scal = dt.  Device pointers.
 int kepler_run_dev(long long pairs, const real_t* const* din, double dt, real_t* const* dout, cudaStream_t st)
@@ -54,6 +90,6 @@ int kepler_run_host(long long pairs, const real_t* const* hin, double dt, real_t
     for (int k = 0; k < 6; ++k)
         TUPAN_CHECK(cudaMemcpyAsync(hout[k], dout[k], bytes, cudaMemcpyDeviceToHost, c.stream), "D2H kepler");
     TUPAN_CHECK(cudaStreamSynchronize(c.stream), "synchronize");
-    return 0;
+    return kepler_limit_check("kepler_solver_kernel");
 }
 }  // namespace tupan

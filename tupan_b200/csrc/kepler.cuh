@@ -11,8 +11,12 @@
 // Laguerre step, at most 64 iterations, failure codes trigger a restart with twice as many
 // sub-steps, period reduction for bound orbits, log-based first guess for hyperbolic ones,
 // r2 > 0 mask returns the state unchanged.  One deliberate difference: the two doubling
-// loops are bounded (MAX_DOUBLINGS) so a pathological pair cannot hang the GPU; the
-// reference would spin forever in the same situation.
+// loops are bounded (at most 2^MAX_DOUBLINGS sub-steps) so a pathological pair cannot hang
+// the GPU.  The reference doubles without bound: for SOFTENED tight binaries its energy
+// check (:533-606) drives it to 10^6 .. 10^9 sequential sub-steps (measured with the oracle:
+// eps2 = 1e-8, a ~ 1e-3, dt = 0.37 -> n = 2^30, 6 minutes on a host core).  When the bound is
+// hit the pair is counted in kepler_limit_hits and the host entry points fail loudly
+// (tupan_cuda_last_error) instead of returning an unconverged state silently.
 #pragma once
 #include "ops.cuh"
 
@@ -37,7 +41,9 @@ template <typename T> struct KeplerTol;
 template <> struct KeplerTol<double> { static TUPAN_DEV double value() { return 2.2737367544323205948e-13; } };  // 2^-42
 template <> struct KeplerTol<float>  { static TUPAN_DEV float value() { return 1.52587890625e-5f; } };           // 2^-16
 
-enum { KEPLER_MAXITER = 64, MAX_DOUBLINGS = 12 };
+enum { KEPLER_MAXITER = 64, MAX_DOUBLINGS = 16 };
+
+__device__ unsigned int kepler_limit_hits = 0;   // pairs that ran into MAX_DOUBLINGS (this TU only)
 
 template <typename T> TUPAN_DEV int sgn(T x) { return (x > T(0)) - (x < T(0)); }
 
@@ -160,8 +166,9 @@ template <typename T> TUPAN_DEV State<T> kepler_substep(T dt, T m, T e2, const S
 {
     State<T> p = p0;
     int n = 1;
+    bool bad = false;
     for (int level = 0; level <= MAX_DOUBLINGS; ++level) {
-        bool bad = false;
+        bad = false;
         p = p0;
         const T h = dt / T(n);
         for (int i = 0; i < n; ++i) {
@@ -170,6 +177,7 @@ template <typename T> TUPAN_DEV State<T> kepler_substep(T dt, T m, T e2, const S
         if (!bad) break;
         n *= 2;
     }
+    if (bad) atomicAdd(&kepler_limit_hits, 1u);
     return p;
 }
 
@@ -194,9 +202,10 @@ template <typename T> __device__ __noinline__ State<T> kepler_propagate(T dt, T 
     const T tol = T(64) * KeplerTol<T>::value();
     if (T(2) * k_abs(e1 - e0) < tol * (u1 + u0)) return p;
     int n = 1;
+    bool bad = true;
     for (int level = 0; level < MAX_DOUBLINGS; ++level) {
         n *= 2;
-        bool bad = false;
+        bad = false;
         p = p0;
         const T h = dt / T(n);
         for (int i = 0; i < n; ++i) {
@@ -206,6 +215,7 @@ template <typename T> __device__ __noinline__ State<T> kepler_propagate(T dt, T 
         }
         if (!bad) break;
     }
+    if (bad) atomicAdd(&kepler_limit_hits, 1u);
     return p;
 }
 
@@ -214,9 +224,8 @@ template <typename T> TUPAN_DEV void twobody_leapfrog(T dt, T m, T e2, State<T>&
 {
     const T half = dt / T(2);
     p.x = fma(p.vx, half, p.x); p.y = fma(p.vy, half, p.y); p.z = fma(p.vz, half, p.z);
-    T x = e2;
-    x = fma(p.x, p.x, x); x = fma(p.y, p.y, x); x = fma(p.z, p.z, x);
-    const InvR<T> w = soft_inv(x, nonzero3(p.x, p.y, p.z));
+    T r2 = p.x * p.x; r2 = fma(p.y, p.y, r2); r2 = fma(p.z, p.z, r2);
+    const InvR<T> w = soft_inv<true>(r2 + e2, r2);
     const T g = -(m * w.r3) * dt;
     p.vx = fma(g, p.x, p.vx); p.vy = fma(g, p.y, p.vy); p.vz = fma(g, p.z, p.vz);
     p.x = fma(p.vx, half, p.x); p.y = fma(p.vy, half, p.y); p.z = fma(p.vz, half, p.z);

@@ -3,8 +3,12 @@
 // Each Op states which reference kernel it replaces (file:line in tupan/lib/src) and the
 // reference's own flops-per-pair convention (its "Total flop count" comments), which is the
 // convention bench.py reports rooflines in.  The arithmetic is arranged for the GPU (FMA
-// chains, rsqrt seed + one cubic step, masks kept in predicates) and therefore differs from
-// the reference in rounding, not in meaning: results agree to ~1e-15 per pair (fp64).
+// chains, rsqrt seed + one cubic step, mask read off the exponent of r2) and therefore differs
+// from the reference in rounding, not in meaning: results agree to ~1e-15 per pair (fp64).
+//
+// Every masked kernel computes r2 = rx^2 + ry^2 + rz^2 on its own and x = r2 + (ie2 + je2):
+// one FP64 instruction more than folding e2 into the FMA chain, but the mask then costs two
+// integer instructions instead of seven (common.cuh) -- a net gain of ~8 % on B200.
 //
 // Caller array order (libtupan.h): 8-array kernels pass  m, rx, ry, rz, e2, vx, vy, vz.
 #pragma once
@@ -68,10 +72,10 @@ template <typename T> struct PhiOp {
     static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
     {
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
-        T x = s[IE] + row[J5_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
-        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
-        a[0] = fma(-row[JM], w.r1, a[0]);
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J5_E2]);
+        T r1 = rsqrt_scaled<true>(x, r2, T(1), T(0.5), T(0.375));
+        a[0] = fma(-row[JM], r1, a[0]);
     }
     static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
     static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
@@ -98,11 +102,11 @@ template <typename T> struct AccOp {
     static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
     {
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
-        T x = s[IE] + row[J5_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
-        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
-        T g = row[JM] * w.r3;
-        a[0] = fma(-g, rx, a[0]); a[1] = fma(-g, ry, a[1]); a[2] = fma(-g, rz, a[2]);
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J5_E2]);
+        InvR<T> w = soft_inv<false>(x, r2);
+        T g = -(row[JM] * w.r3);
+        a[0] = fma(g, rx, a[0]); a[1] = fma(g, ry, a[1]); a[2] = fma(g, rz, a[2]);
     }
     static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
     static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
@@ -114,13 +118,16 @@ template <typename T> struct AccOp {
 // =======================================================================================
 // acc_jerk -- replaces acc_jerk_kernel (acc_jerk_kernel.c:5-61, core
 // acc_jerk_kernel_common.h:7-56); 42 flop/pair by the reference's count.
-// FP64-pipe instructions per pair here: 6 (differences) + 4 (r2+e2) + 3 (r.v) + 5 (rsqrt
-// step) + 2 (1/r^2, 1/r^3) + 2 (alpha) + 1 (m/r^3) + 9 (FMA updates) = 32.
+// FP64-pipe instructions per pair here: 6 (differences) + 3 (r2) + 2 (e2, x) + 3 (r.v) + 5
+// (rsqrt step) + 2 (3/x, 3 sqrt3 x^-3/2) + 1 (alpha) + 1 (g) + 9 (FMA updates) = 32, plus
+// 2 LDS.128, MUFU, ISETP, SEL.  Two constant factors ride for free: the rsqrt step returns
+// sqrt(3/x), so its square is the 3/x of alpha = 3 (r.v)/x, and the 3 sqrt 3 that its cube
+// carries is divided out of the mass once, in pack_j (row[JM] = mj / (3 sqrt 3)).
 // =======================================================================================
 template <typename T> struct AccJerkOp {
     typedef T real;
     typedef NoParams Params;
-    enum { NI = 7, NJ = 8, NA = 6, NO = 6, WPT = 2, UNROLL = 4 };
+    enum { NI = 7, NJ = 8, NA = 6, NO = 6, WPT = 2, UNROLL = 8 };
     enum { NJP = round_up(NJ, Vec16<T>::N) };
     enum { IX, IY, IZ, IE, IVX, IVY, IVZ };
     static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
@@ -128,21 +135,28 @@ template <typename T> struct AccJerkOp {
         s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
         s[IVX] = a[5][i]; s[IVY] = a[6][i]; s[IVZ] = a[7][i];
     }
-    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row8(j, r, row); }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP])
+    {
+        pack_row8(j, r, row);
+        row[JM] = row[JM] * T(0.19245008972987526);          // 1 / (3 sqrt 3)
+    }
     static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
     static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params&)
     {
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
         T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
-        T x = s[IE] + row[J8_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J8_E2]);
         T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
-        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
-        T alpha = (T(3) * w.r2) * rv;
+        // sqrt(3/x): k = sqrt 3, k/2, 3k/8
+        T r1 = rsqrt_scaled<false>(x, r2, T(1.7320508075688772), T(0.86602540378443865), T(0.64951905283832900));
+        T q2 = r1 * r1;                    // 3/x
+        T q3 = q2 * r1;                    // 3 sqrt3 x^-3/2
+        T alpha = q2 * rv;                 // 3 (r.v)/x
+        T g = -(row[JM] * q3);             // -mj x^-3/2
         vx = fma(-alpha, rx, vx); vy = fma(-alpha, ry, vy); vz = fma(-alpha, rz, vz);
-        T g = row[JM] * w.r3;
-        a[0] = fma(-g, rx, a[0]); a[1] = fma(-g, ry, a[1]); a[2] = fma(-g, rz, a[2]);
-        a[3] = fma(-g, vx, a[3]); a[4] = fma(-g, vy, a[4]); a[5] = fma(-g, vz, a[5]);
+        a[0] = fma(g, rx, a[0]); a[1] = fma(g, ry, a[1]); a[2] = fma(g, rz, a[2]);
+        a[3] = fma(g, vx, a[3]); a[4] = fma(g, vy, a[4]); a[5] = fma(g, vz, a[5]);
     }
     static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
     static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
@@ -183,14 +197,14 @@ template <typename T> struct SnapCrackleOp {
         T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
         T ax = s[IAX] - row[J14_AX], ay = s[IAY] - row[J14_AY], az = s[IAZ] - row[J14_AZ];
         T jx = s[IJX] - row[J14_JX], jy = s[IJY] - row[J14_JY], jz = s[IJZ] - row[J14_JZ];
-        T x = s[IE] + row[J8_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J8_E2]);
         T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
         T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
         T rj = rx * jx; rj = fma(ry, jy, rj); rj = fma(rz, jz, rj);
         T ra = rx * ax; ra = fma(ry, ay, ra); ra = fma(rz, az, ra);
         T va = vx * ax; va = fma(vy, ay, va); va = fma(vz, az, va);
-        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        InvR<T> w = soft_inv<false>(x, r2);
 
         // same recurrences as snap_crackle_kernel_common.h:63-84
         T alpha = rv * w.r2;
@@ -245,17 +259,17 @@ template <typename T> struct TstepOp {
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
         T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
         T m = s[IM] + row[JM];
-        T x = s[IE] + row[J8_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J8_E2]);
         T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
         T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
-        const bool ok = nonzero3(rx, ry, rz);
-        InvR<T> w = soft_inv(x, ok);
+        InvR<T> w = soft_inv<true>(x, r2);
         // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv
         T phi = m * w.r1;
         T w2 = w.r2 * fma(T(2), phi, v2);
         T gamma = w.r2 * fma(T(2) * w.r2, phi, w2);
-        gamma *= p.eta * rsqrt_masked(w2, ok);   // masked pair: seed 0 -> gamma 0 -> w2 stays 0
+        // masked pair: w2 is exactly 0, its own exponent masks the seed -> gamma 0 -> w2 stays 0
+        gamma *= p.eta * rsqrt_scaled<true>(w2, w2, T(1), T(0.5), T(0.375));
         w2 = fma(-gamma, rv, w2);
         a[0] += w2;
         a[1] = rmax(w2, a[1]);
@@ -295,9 +309,9 @@ template <typename T> struct NregXOp {
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
         T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
         rx = fma(vx, p.dt, rx); ry = fma(vy, p.dt, ry); rz = fma(vz, p.dt, rz);
-        T x = s[IE] + row[J8_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
-        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J8_E2]);
+        InvR<T> w = soft_inv<true>(x, r2);
         T mj = row[JM];
         T g = mj * w.r3;
         a[0] = fma(mj, rx, a[0]); a[1] = fma(mj, ry, a[1]); a[2] = fma(mj, rz, a[2]);

@@ -261,20 +261,64 @@ template <class Op> struct Tune {
     enum { NT = 256, TJ = 128, STAGES = 4, NT_SPLIT = 128 };
 };
 
+// CTAs of the throughput kernel the chip holds at once (occupancy x SMs), cached per Op.
+template <class Op>
+inline int throughput_slots(const DeviceInfo& dev)
+{
+    typedef Tune<Op> U;
+    static int occ = 0;
+    if (occ == 0) {
+        auto k = pair_kernel<Op, U::NT, Op::WPT, U::TJ, U::STAGES, false>;
+        const size_t smem = PairSmem<Op, U::TJ, U::STAGES>::BYTES;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, U::NT, smem) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = 1;
+        }
+        occ = n;
+    }
+    return occ * dev.sm_count;
+}
+
+// Launch shape.
+//   * throughput shape (WPT particles per thread, unrolled j loop) whenever the i-blocks times
+//     the j chunks available can fill every CTA slot of the chip; the number of j chunks is
+//     then chosen so that the CTA count is (nearly) a whole number of waves -- all CTAs do
+//     the same work, so a partial last wave is pure loss (N = 2^20 / 8 GPUs: 256 i-blocks on
+//     296 slots would idle 14 % of the chip; 37 chunks make it 32 full waves);
+//   * lane split (several lanes per particle) for small ni.
 template <class Op>
 inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
 {
+    typedef Tune<Op> U;
     Plan p = {0, 0, 1};
+    const int TJ = U::TJ;
+    const long long IB = (long long)U::NT * Op::WPT;
+    const long long iblocks = (ni + IB - 1) / IB;
+    const long long slots = throughput_slots<Op>(dev);
+    long long maxg = nj / (8 * TJ);               // a chunk is at least 8 tiles
+    if (maxg > 64) maxg = 64;
+    if (maxg < 1) maxg = 1;
+    if (iblocks * maxg >= slots && ni * 10 >= iblocks * IB * 9) {
+        double best = 0.0;
+        for (long long g = 1; g <= maxg; ++g) {
+            const long long ctas = iblocks * g;
+            const long long waves = (ctas + slots - 1) / slots;
+            const double eff = (double)ctas / (double)(waves * slots);
+            if (eff > best + 1e-9) { best = eff; p.jg = (int)g; }
+            if (eff >= 0.985) { p.jg = (int)g; break; }
+        }
+        return p;
+    }
     const long long resident = (long long)dev.sm_count * 512;  // threads we want in flight
-    const int TJ = Tune<Op>::TJ;
-    if ((ni + Op::WPT - 1) / Op::WPT >= resident) return p;     // big ni: throughput shape
     p.lane_split = 1;
     // lanes per particle: enough to fill the chip, never more than a tile can feed
     while (p.js_log2 < 5 && (ni << p.js_log2) < resident && (TJ >> (p.js_log2 + 1)) >= 4) p.js_log2++;
     long long threads = ni << p.js_log2;
     long long want = (resident + threads - 1) / threads;        // j chunks to fill the rest
-    long long maxg = (nj + 4 * TJ - 1) / (4 * TJ);              // >= 4 tiles per chunk
-    if (want > maxg) want = maxg;
+    long long mg = (nj + 4 * TJ - 1) / (4 * TJ);                // >= 4 tiles per chunk
+    if (want > mg) want = mg;
     if (want > 64) want = 64;
     if (want < 1) want = 1;
     p.jg = (int)want;

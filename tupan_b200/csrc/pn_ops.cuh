@@ -177,9 +177,9 @@ template <typename T, int LEVEL> struct PNAccOp {
         if (LEVEL < 2) return;
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
         T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
-        T x = s[IE] + row[J8_E2];
-        x = fma(rx, rx, x); x = fma(ry, ry, x); x = fma(rz, rz, x);
-        InvR<T> w = soft_inv(x, nonzero3(rx, ry, rz));
+        T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
+        T x = r2 + (s[IE] + row[J8_E2]);
+        InvR<T> w = soft_inv<true>(x, r2);
 
         PNScalars<T> q;
         q.mi = s[IM]; q.mj = row[JM]; q.ir = w.r1; q.ir2 = w.r2;
