@@ -34,8 +34,10 @@ for n in (5000, 40001):
         torch.cuda.synchronize()
         for name in device.KERNEL_OUTPUTS[kernel]:
             a, b = out[name].cpu().numpy(), ref[name][sk.lo:sk.hi].cpu().numpy()
-            err = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
-            assert err < 1e-11, (kernel, name, n, err)
+            # summation order differs (local/remote sweeps, other chunking): compare on the
+            # scale of the array, not per component (components cancel, SURVEY.md 7)
+            err = np.max(np.abs(a - b)) / np.max(np.abs(b))
+            assert err < 1e-12, (kernel, name, n, err)
 dist.barrier()
 if rank == 0:
     print("SHARDED-GPU-OK world=%%d" %% world)
@@ -57,4 +59,5 @@ def test_sharded_matches_single_gpu(world):
         path = f.name
     cmd = cmd[:-2] + [path]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0 and "SHARDED-GPU-OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+    tail = "\n".join(l for l in (p.stdout + p.stderr).splitlines() if "Error" in l or "assert" in l or "File" in l)
+    assert p.returncode == 0 and "SHARDED-GPU-OK" in p.stdout, tail[-3000:]
