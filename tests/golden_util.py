@@ -44,3 +44,20 @@ def load_kepler(prec):
         outs = {k.split("/")[2]: z[k] for k in z.files if k.startswith("%d/out/" % c)}
         cases.append((ins, float(z["%d/dt" % c]), outs))
     return cases
+
+
+def load_integrator_cases(prec, name="integrators"):
+    """-> {case: (inputs dict, outputs dict, meta)}; meta = eta, t_end, steps, t_final, ke0, pe0,
+    ke1, pe1 (tests/golden/make_golden_integrators.py)."""
+    z = np.load(os.path.join(GOLDEN, "%s_%s.npz" % (name, TAGS[prec])))
+    cases = {}
+    for key in z.files:
+        case, rest = key.split("/", 1)
+        ins, outs, meta = cases.setdefault(case, ({}, {}, [None]))
+        if rest.startswith("in/"):
+            ins[rest[3:]] = z[key]
+        elif rest.startswith("out/"):
+            outs[rest[4:]] = z[key]
+        else:
+            meta[0] = z[key]
+    return {k: (i, o, m[0]) for k, (i, o, m) in cases.items()}
