@@ -208,6 +208,68 @@ int tupan_cuda_sm_count(void);
 int tupan_cuda_fma_peak(double ms, double *tflops, double *sm_mhz_effective);
 int tupan_cuda_real_bytes(void);                   /* sizeof(REAL): 8 or 4 */
 
+/* ------------------------------------------------------------------------------------ */
+/* Part 3 -- O(N) integrator updates on device-resident state      */
+/* ------------------------------------------------------------------------------------ */
+
+/* The reference advances the state on the host with numpy between two kernel calls and
+ * reads min|tstep| back every step.  These entry points do the same arithmetic (same
+ * operation order, one rounding per operation, no FMA contraction) on device arrays, with
+ * the step size held in a device control block of TUPAN_CTL_SIZE doubles, so that a whole
+ * step is enqueued on one stream with no host round trip.  All are asynchronous on `stream`. */
+enum tupan_ctl {
+    TUPAN_CTL_T_CURR = 0,   /* current time (the reference's class attribute t_curr)          */
+    TUPAN_CTL_TAU = 1,      /* step chosen by tupan_cuda_step_begin_dev (0 once done)          */
+    TUPAN_CTL_T_END = 2,    /* set by the caller                                               */
+    TUPAN_CTL_ETA = 3,      /* set by the caller                                               */
+    TUPAN_CTL_NSTEPS = 4,   /* steps completed                                                 */
+    TUPAN_CTL_DONE = 5,     /* 1 when |t_curr| >= |t_end|: further steps are no-ops            */
+    TUPAN_CTL_TAU_BASE = 6, /* Base.get_base_tstep of the step                                 */
+    TUPAN_CTL_MIN_TS = 7,   /* the minimum time-step the block step was derived from           */
+    TUPAN_CTL_SIZE = 8
+};
+
+/* replaces Base.get_base_tstep + get_min_block_tstep (integrator/__init__.py:48-78):
+ * tau = copysign(min(|t_end|-|t_curr|, |eta|), eta); with d_min_tstep != NULL (a device
+ * double holding min_i |tstep_i|) the power-of-two block step commensurate with t_curr. */
+int tupan_cuda_step_begin_dev(void *d_ctl, const void *d_min_tstep, void *stream);
+
+/* replaces H2/H4/H6/H8.epredict (integrator/hermite.py:25-43,75-91,127-158,202-242) after the
+ * force evaluation: rv = {rx ry rz vx vy vz} is advanced in place, its old value is saved in
+ * rv0; d0 = {ax ay az [jx jy jz [sx sy sz [cx cy cz]]]} (order/2 triples) of the old state. */
+int tupan_cuda_hermite_predict_dev(int order, long long n, void *const *rv, void *const *rv0,
+                                   const void *const *d0, const void *d_ctl, void *stream);
+/* replaces H*.ecorrect (hermite.py:45-57,93-121,160-196,244-283) after the force evaluation
+ * of the predicted state (derivatives d1) */
+int tupan_cuda_hermite_correct_dev(int order, long long n, void *const *rv, void *const *rv0,
+                                   const void *const *d0, const void *const *d1, const void *d_ctl,
+                                   void *stream);
+/* y[k] += x[k] * REAL(c_inner * (c_outer * tau)), k < narr <= 6; tau = ctl[TAU] (1 if d_ctl
+ * is NULL).  Replaces drift_n / kick_n (integrator/sia.py:64-84), the half drifts and the
+ * += (dr, dv) of sakura_step (integrator/sakura.py:25-48). */
+int tupan_cuda_axpy_dev(int narr, long long n, void *const *y, const void *const *x, double c_outer,
+                        double c_inner, const void *d_ctl, void *stream);
+/* y[k] = x[k] / REAL(denom): r = mr / mtot, v = mv / mtot of nreg_x / nreg_v (nreg.py:28-30,51-53) */
+int tupan_cuda_scale_dev(int narr, long long n, void *const *y, const void *const *x, double denom,
+                         void *stream);
+/* t_curr += tau; tstep[:] = tau; time += tau; nstep += 1 (hermite.py:398-401; sia.py:1105-1113;
+ * sakura.py:136-139).  Array pointers may be NULL. */
+int tupan_cuda_step_end_dev(long long n, void *d_time, void *d_nstep, void *d_tstep, void *d_ctl,
+                            void *stream);
+
+/* deterministic reductions over particles; the result is ONE double written to d_out */
+enum tupan_reduction {
+    TUPAN_RED_SUM = 0,       /* sum x0                                (u, mk: nreg.py:31,54)     */
+    TUPAN_RED_KINETIC = 1,   /* sum 0.5 m (vx^2+vy^2+vz^2)            (body.py:262-275)          */
+    TUPAN_RED_HALF_DOT = 2,  /* 0.5 sum x0 x1  (m, phi)               (body.py:294-306)          */
+    TUPAN_RED_SAKURA_DT = 3, /* eta / sqrt(1 + max((eta/x0)^2-(eta/x1)^2)), param = eta
+                                (tstep, tstepij)                      (sakura.py:100-110)        */
+    TUPAN_RED_ABS_MIN = 4,   /* min |x0|                              (body.py:364-368)          */
+    TUPAN_RED_ABS_MAX = 5    /* max |x0|                              (body.py:370-374)          */
+};
+int tupan_cuda_reduce_dev(int what, long long n, const void *const *arrays, double param, void *d_out,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,22 @@ PART2 = {
     "tupan_cuda_fma_peak": (ctypes.c_int, [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
     "tupan_cuda_real_bytes": (ctypes.c_int, []),
+    # Part 3: O(N) integrator updates on device-resident state
+    "tupan_cuda_step_begin_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_hermite_predict_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                      ctypes.c_void_p]),
+    "tupan_cuda_hermite_correct_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_axpy_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_scale_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_double, ctypes.c_void_p]),
+    "tupan_cuda_step_end_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_reduce_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _PREC = {

@@ -14,7 +14,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-UNITS = ["abi", "context", "k_newton", "k_snap", "k_nreg", "k_pn", "k_sakura"]
+UNITS = ["abi", "context", "k_newton", "k_snap", "k_nreg", "k_pn", "k_sakura", "k_update"]
+# k_update evaluates the O(N) integrator updates in the reference's numpy operation order, one
+# rounding per operation: no FMA contraction in that unit.
+UNIT_FLAGS = {"k_update": ["-fmad=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -35,7 +38,8 @@ def _compile(args):
     obj = os.path.join(LIBDIR, "obj", "%s_%s.o" % (unit, tag))
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
         return unit, tag, "cached", ""
-    cmd = [NVCC] + FLAGS + (["-DTUPAN_FP64"] if tag == "fp64" else []) + ["-c", src, "-o", obj]
+    cmd = ([NVCC] + FLAGS + UNIT_FLAGS.get(unit, []) + (["-DTUPAN_FP64"] if tag == "fp64" else [])
+           + ["-c", src, "-o", obj])
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s (%s):\n%s\n%s" % (unit, tag, p.stdout, p.stderr))

@@ -1,0 +1,463 @@
+"""Device-resident integrators with the interface of the reference's ``tupan.integrator``.
+
+``Integrator(eta, time, ps, method=...)`` mirrors ``tupan/integrator/__init__.py:102-157``:
+``initialize / evolve_step(t_end) / finalize``, ``.time``, ``.particle_system``; the same
+method names (``hermite2..8``, ``ahermite2..8``, ``siaXYs|a.dkd|kdk``, ``nreg``, ``anreg``,
+``sakura``, ``asakura``).  What differs is where the state lives: the reference keeps numpy
+arrays on the host, copies the particle system every step (``ps.copy()``, hermite.py:29) and
+reads ``abs(ps.tstep).min()`` back to choose the step; here the SoA state is uploaded once
+and stays in HBM, every O(N) update is one of the kernels of ``csrc/k_update.cu`` (Part 3 of
+``include/libtupan_cuda.h``), the force evaluations are the pair kernels (device entry
+points, or the i-sharded multi-GPU path when a process group is given), and the step size is
+derived on the device -- a whole Hermite / SIA step is enqueued on one stream without a host
+round trip.  ``.time`` / ``.particle_system`` synchronise and download.
+
+The O(N) updates follow the reference's operation order exactly, so the only numerical
+difference from the reference is the summation order inside the pair kernels.
+
+Not covered here (raises): hierarchical ``sia..h`` splitting and post-Newtonian kicks.
+There is no CPU path: the CUDA library must be loadable and a GPU present.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import backend
+from .device import KERNEL_INPUTS, KERNEL_OUTPUTS, run as run_kernel
+from .sharded import ShardedKernel, shard_bounds
+
+CTL_T_CURR, CTL_TAU, CTL_T_END, CTL_ETA, CTL_NSTEPS, CTL_DONE, CTL_TAU_BASE, CTL_MIN_TS = range(8)
+RED_SUM, RED_KINETIC, RED_HALF_DOT, RED_SAKURA_DT, RED_ABS_MIN, RED_ABS_MAX = range(6)
+
+R3, V3, A3, J3, S3, C3 = (("rx", "ry", "rz"), ("vx", "vy", "vz"), ("ax", "ay", "az"),
+                          ("jx", "jy", "jz"), ("sx", "sy", "sz"), ("cx", "cy", "cz"))
+DERIVS = A3 + J3 + S3 + C3
+
+# (A, B) of the reference's SIAxy.coefs (integrator/sia.py:302-303, 360-362, 425-428, 497-501,
+# 576-581, 662-668, 755-762, 855-864; Yoshida 1990, Omelyan et al. 2003, Blanes & Moan 2002,
+# Kahan & Li 1997)
+SIA_COEFS = {
+    "sia21": ([1.0], [0.5]),
+    "sia22": ([0.5], [0.1931833275037836, 0.6136333449924328]),
+    "sia43": ([1.3512071919596575, -1.7024143839193150], [0.6756035959798288, -0.17560359597982877]),
+    "sia44": ([0.7123418310626056, -0.21234183106260562],
+              [0.1786178958448091, -0.06626458266981843, 0.7752933736500186]),
+    "sia45": ([-0.0844296195070715, 0.354900057157426, 0.459059124699291],
+              [0.2750081212332419, -0.1347950099106792, 0.35978688867743724]),
+    "sia46": ([0.209515106613362, -0.143851773179818, 0.434336666566456],
+              [0.0792036964311957, 0.353172906049774, -0.0420650803577195, 0.21937695575349958]),
+    "sia67": ([0.7845136104775573, 0.23557321335935813, -1.177679984178871, 1.3151863206839112],
+              [0.39225680523877865, 0.5100434119184577, -0.47105338540975644, 0.06875316825252015]),
+    "sia69": ([0.39103020330868477, 0.334037289611136, -0.7062272811875614, 0.08187754964805945,
+               0.7985644772393624],
+              [0.19551510165434238, 0.3625337464599104, -0.1860949957882127, -0.31217486576975095,
+               0.44022101344371095]),
+}
+
+
+def operator_sequence(outer, inner):
+    """The palindromic composition every SIAxy.dkd / .kdk / .bridge_sf spells out (e.g.
+    sia.py:441-453): the two weight lists interleaved starting with `outer`, mirrored about
+    the last one.  -> [(is_outer, weight)]"""
+    seq = []
+    for i in range(max(len(outer), len(inner))):
+        if i < len(outer):
+            seq.append((True, outer[i]))
+        if i < len(inner):
+            seq.append((False, inner[i]))
+    return seq + seq[-2::-1]
+
+
+class DeviceState(object):
+    """SoA particle arrays in HBM (attribute names of particles/body.py:26-39)."""
+
+    BASE = ("mass", "eps2", "rx", "ry", "rz", "vx", "vy", "vz", "time", "tstep")
+
+    def __init__(self, ps, device, lo=0, hi=None):
+        self.device = torch.device(device)
+        self.lo, self.hi = lo, ps.n if hi is None else hi
+        self.n = self.hi - self.lo
+        self.np_dtype = np.dtype(ps.mass.dtype)
+        self.dtype = torch.float64 if self.np_dtype == np.float64 else torch.float32
+        self.t = {}
+        for k in self.BASE:
+            self.t[k] = self._up(np.asarray(getattr(ps, k), self.np_dtype))
+        itype = np.int64 if self.np_dtype == np.float64 else np.int32      # same bits as the UINT array
+        self.t["nstep"] = self._up(np.ascontiguousarray(getattr(ps, "nstep")).view(itype))
+
+    def _up(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a[self.lo:self.hi])).to(self.device).contiguous()
+
+    def need(self, *names):
+        for k in names:
+            if k not in self.t:
+                self.t[k] = torch.zeros(self.n, dtype=self.dtype, device=self.device)
+        return [self.t[k] for k in names]
+
+    def __getitem__(self, k):
+        return self.t[k]
+
+    def download(self, ps, names=None):
+        """Write the device arrays back into the host container's arrays (in place)."""
+        for k, t in self.t.items():
+            if names is not None and k not in names:
+                continue
+            if k.endswith("0") or k.startswith("_"):
+                continue
+            h = t.cpu().numpy()
+            if k not in ps.__dict__:
+                if not hasattr(ps, "register_auxiliary_attribute"):
+                    continue
+                ps.register_auxiliary_attribute(k, "real")
+            dst = getattr(ps, k)
+            if k == "nstep":
+                dst = dst.view(h.dtype)
+            dst[self.lo:self.hi] = h
+
+
+class _Lib(object):
+    """Thin caller of Part 3 of include/libtupan_cuda.h on torch tensors."""
+
+    def __init__(self, prec):
+        self.lib = backend.require_gpu(prec)
+        self._ptrs = {}
+
+    def ptrs(self, tensors):
+        key = tuple(t.data_ptr() for t in tensors)
+        p = self._ptrs.get(key)
+        if p is None:
+            for t in tensors:
+                if not (t.is_cuda and t.is_contiguous()):
+                    raise TypeError("contiguous CUDA tensors required")
+            p = self._ptrs[key] = (ctypes.c_void_p * len(key))(*key)
+        return p
+
+    @staticmethod
+    def stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def ok(self, rc, what):
+        if rc != 0:
+            backend.check(self.lib, what)
+            raise backend.TupanCudaError("%s failed with code %d" % (what, rc))
+
+    def step_begin(self, ctl, dmin=None):
+        self.ok(self.lib.tupan_cuda_step_begin_dev(ctl.data_ptr(), dmin.data_ptr() if dmin is not None else None,
+                                                   self.stream()), "step_begin")
+
+    def predict(self, order, n, rv, rv0, d0, ctl):
+        self.ok(self.lib.tupan_cuda_hermite_predict_dev(order, n, self.ptrs(rv), self.ptrs(rv0), self.ptrs(d0),
+                                                        ctl.data_ptr(), self.stream()), "hermite_predict")
+
+    def correct(self, order, n, rv, rv0, d0, d1, ctl):
+        self.ok(self.lib.tupan_cuda_hermite_correct_dev(order, n, self.ptrs(rv), self.ptrs(rv0), self.ptrs(d0),
+                                                        self.ptrs(d1), ctl.data_ptr(), self.stream()),
+                "hermite_correct")
+
+    def axpy(self, n, y, x, c_outer=1.0, c_inner=1.0, ctl=None):
+        self.ok(self.lib.tupan_cuda_axpy_dev(len(y), n, self.ptrs(y), self.ptrs(x), c_outer, c_inner,
+                                             ctl.data_ptr() if ctl is not None else None, self.stream()), "axpy")
+
+    def scale(self, n, y, x, denom):
+        self.ok(self.lib.tupan_cuda_scale_dev(len(y), n, self.ptrs(y), self.ptrs(x), denom, self.stream()), "scale")
+
+    def step_end(self, n, time, nstep, tstep, ctl):
+        self.ok(self.lib.tupan_cuda_step_end_dev(n, time.data_ptr(), nstep.data_ptr(), tstep.data_ptr(),
+                                                 ctl.data_ptr(), self.stream()), "step_end")
+
+    def reduce(self, what, n, arrays, out, param=0.0):
+        self.ok(self.lib.tupan_cuda_reduce_dev(what, n, self.ptrs(arrays), param, out.data_ptr(), self.stream()),
+                "reduce")
+
+
+class Integrator(object):
+    PROVIDED_METHODS = (["hermite%d" % o for o in (2, 4, 6, 8)] + ["ahermite%d" % o for o in (2, 4, 6, 8)]
+                        + ["%s%s.%s" % (s, k, o) for s in sorted(SIA_COEFS) for k in "sa" for o in ("dkd", "kdk")]
+                        + ["nreg", "anreg", "sakura", "asakura"])
+
+    def __init__(self, eta, time, ps, method=None, device=None, group=None, pn_order=0, clight=None, **kwargs):
+        if method not in self.PROVIDED_METHODS:
+            if method and method.startswith("sia") and "h." in method:
+                raise NotImplementedError("hierarchical SIA splitting (%s) is not device-resident yet" % method)
+            raise ValueError("Unexpected integration method: %r. Provided methods: %s"
+                             % (method, self.PROVIDED_METHODS))
+        if pn_order:
+            raise NotImplementedError("post-Newtonian kicks are not device-resident yet")
+        self.reporter = kwargs.pop("reporter", None)
+        for k in ("viewer", "dumpper", "dump_freq", "gl_freq"):
+            kwargs.pop(k, None)
+        if kwargs:
+            raise TypeError("Integrator.__init__ received unexpected keyword arguments: %s." % ", ".join(kwargs))
+        self.eta, self.method, self.ps = float(eta), method, ps
+        self.group = group
+        self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        bounds = shard_bounds(ps.n, self.world)
+        self.st = DeviceState(ps, self.device, bounds[self.rank], bounds[self.rank + 1])
+        self.n_total = ps.n
+        self.prec = "float64" if self.st.dtype == torch.float64 else "float32"
+        self.L = _Lib(self.prec)
+        self.ctl = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.ctl[CTL_T_CURR] = float(time)
+        self.ctl[CTL_ETA] = self.eta
+        self._t_end = None
+        self._scalar = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._sharded = {}
+        self.is_initialized = False
+        self.adaptive = method.startswith("a") or (method.startswith("sia") and method[5] == "a")
+        if "hermite" in method:
+            self.order = int(method[-1])
+            self._step = self._hermite_step
+        elif method.startswith("sia"):
+            self._step = self._sia_step
+            A, B = SIA_COEFS[method[:5]]
+            kdk = method.endswith("kdk")
+            # bridge_sf with an empty fast set (sia.py:341-352): only the sf_drifts act, each
+            # one evolve(slow, B_i * tau); evolve = the dkd / kdk composition (sia.py:308-337)
+            self._bridge = [w for outer, w in operator_sequence(B, A) if outer]
+            self._evolve = [(outer != kdk, w) for outer, w in operator_sequence(B, A)]   # (is_drift, weight)
+        elif "sakura" in method:
+            self._step = self._sakura_step
+        else:
+            self._step = self._nreg_step
+            self._nreg = None
+
+    # ---- forces --------------------------------------------------------------------------
+    def force(self, kernel, out_names, scalars=(), inputs=None):
+        """out_names: tensors (by state name) receiving KERNEL_OUTPUTS[kernel], in order."""
+        st = self.st
+        outs = st.need(*out_names)
+        out = dict(zip(KERNEL_OUTPUTS[kernel], outs))
+        src = {a: st[(inputs or {}).get(a, a)] for a in KERNEL_INPUTS[kernel]}
+        if self.world == 1:
+            run_kernel(kernel, src, src, scalars, out)
+        else:
+            sk = self._sharded.get(kernel)
+            if sk is None:
+                sk = self._sharded[kernel] = ShardedKernel(kernel, self.n_total, st.dtype, self.device,
+                                                           group=self.group)
+            sk.evaluate(src, scalars, out)
+
+    def reduce(self, what, names, slot, param=0.0):
+        """Reduction over ALL particles into self._scalar[slot] (device); all-reduced over ranks."""
+        out = self._scalar[slot:slot + 1]
+        self.L.reduce(what, self.st.n, [self.st[k] for k in names], out, param)
+        if self.world > 1:
+            if what in (RED_ABS_MIN,):
+                op = dist.ReduceOp.MIN
+            elif what in (RED_ABS_MAX,):
+                op = dist.ReduceOp.MAX
+            elif what == RED_SAKURA_DT:
+                op = dist.ReduceOp.MIN            # dt = eta/sqrt(1 + max w2) is monotone in the max
+            else:
+                op = dist.ReduceOp.SUM
+            dist.all_reduce(out, op=op, group=self.group)
+        return out
+
+    # ---- reference API ------------------------------------------------------------------------
+    def initialize(self, t_end):
+        if self.reporter:
+            self.reporter.diagnostic_report(self.particle_system)
+        self.is_initialized = True
+
+    def finalize(self, t_end):
+        torch.cuda.synchronize(self.device)
+        hits = self.L.lib.tupan_cuda_kepler_limit_hits()
+        if hits != 0:
+            raise backend.TupanCudaError("%d pair(s) hit the Kepler sub-step bound during the run" % hits)
+
+    def _set_t_end(self, t_end):
+        if self._t_end != t_end:
+            self._t_end = t_end
+            self.ctl[CTL_T_END] = float(t_end)
+
+    def evolve_step(self, t_end):
+        """One step toward t_end, enqueued on the current stream (Base.evolve_step,
+        integrator/__init__.py:80-99).  A step requested at or past t_end is a no-op."""
+        if not self.is_initialized:
+            self.initialize(t_end)
+        self._set_t_end(t_end)
+        self._step()
+        if self.reporter:
+            self.reporter.diagnostic_report(self.particle_system)
+
+    def evolve(self, t_end, check_every=8, max_steps=None):
+        """The driver loop `while abs(time) < t_end: evolve_step(t_end)` (simulation.py:187-201)
+        with the clock read back only every `check_every` steps.  -> steps taken."""
+        while True:
+            for _ in range(check_every):
+                self.evolve_step(t_end)
+            c = self.ctl.cpu()
+            if not (abs(float(c[CTL_T_CURR])) < abs(t_end)):
+                break
+            if max_steps is not None and int(c[CTL_NSTEPS]) >= max_steps:
+                break
+        return int(c[CTL_NSTEPS])
+
+    @property
+    def time(self):
+        return float(self.ctl[CTL_T_CURR].item())
+
+    @property
+    def nsteps(self):
+        return int(self.ctl[CTL_NSTEPS].item())
+
+    @property
+    def particle_system(self):
+        self.st.download(self.ps)
+        return self.ps
+
+    def energies(self):
+        """(kinetic, potential) as particles/body.py:262-306 defines them, reduced on the device."""
+        self.force("phi_kernel", ("phi",))
+        self.reduce(RED_KINETIC, ("mass",) + V3, 2)
+        self.reduce(RED_HALF_DOT, ("mass", "phi"), 3)
+        ke, pe = self._scalar[2:4].cpu().tolist()
+        return ke, pe
+
+    # ---- Hermite (integrator/hermite.py:390-410) ----------------------------------------------
+    def _derivs(self, suffix):
+        o = self.order
+        kernel_out = (A3 if o == 2 else A3 + J3)
+        names = tuple(k + suffix for k in kernel_out)
+        self.force("acc_kernel" if o == 2 else "acc_jerk_kernel", names)
+        if o >= 6:
+            # snap_crackle consumes the a, j just computed for the same state (hermite.py:132-133)
+            alias = {k: k + suffix for k in A3 + J3}
+            self.force("snap_crackle_kernel", tuple(k + suffix for k in S3 + C3), inputs=alias)
+
+    def _begin(self, min_names=None):
+        if min_names is not None:
+            dmin = self.reduce(RED_ABS_MIN, min_names, 0)
+            self.L.step_begin(self.ctl, dmin)
+        else:
+            self.L.step_begin(self.ctl)
+
+    # The raw per-particle criterion goes to a scratch array ("_tstep"): ps.tstep itself holds the
+    # step actually taken (hermite.py:399), also after no-op steps past t_end.
+    def _end(self):
+        st = self.st
+        self.L.step_end(st.n, st["time"], st["nstep"], st["tstep"], self.ctl)
+
+    def _hermite_step(self):
+        st, L, o = self.st, self.L, self.order
+        if self.adaptive:                                  # get_hermite_tstep, hermite.py:343-349
+            self.force("tstep_kernel", ("_tstep", "tstepij"), (self.eta,))
+            self._begin(("_tstep",))
+        else:
+            self._begin()
+        nd = DERIVS[:3 * (o // 2)]
+        rv = st.need(*(R3 + V3))
+        rv0 = st.need(*[k + "0" for k in R3 + V3])
+        d0 = st.need(*[k + "0" for k in nd])
+        d1 = st.need(*nd)
+        self._derivs("0")                                  # epredict: forces of ps0
+        L.predict(o, st.n, rv, rv0, d0, self.ctl)
+        for _ in range(2):                                 # epec(2, ...), hermite.py:59-67
+            self._derivs("")
+            L.correct(o, st.n, rv, rv0, d0, d1, self.ctl)
+        self._end()
+
+    # ---- SIA, shared time-step (integrator/sia.py:1032-1123) ----------------------------------
+    def _sia_step(self):
+        st, L = self.st, self.L
+        if self.n_total <= 2:
+            raise NotImplementedError("n <= 2 goes to the Kepler solver (fewbody.py); use tupan_cuda_kepler_dev")
+        if self.adaptive:
+            self.force("tstep_kernel", ("_tstep", "tstepij"), (self.eta,))
+            self._begin(("_tstep",))
+        else:
+            self._begin()
+        r, v, a = st.need(*R3), st.need(*V3), st.need(*A3)
+        for wb in self._bridge:
+            for is_drift, w in self._evolve:
+                if is_drift:
+                    L.axpy(st.n, r, v, wb, w, self.ctl)    # drift_n
+                else:
+                    self.force("acc_kernel", A3)           # kick = set_acc + kick_n
+                    L.axpy(st.n, v, a, wb, w, self.ctl)
+        self._end()
+
+    # ---- Sakura (integrator/sakura.py:22-50, 100-147) -------------------------------------------
+    def _tau_host(self):
+        return float(self.ctl[CTL_TAU].item())
+
+    def _sakura_step(self):
+        st, L = self.st, self.L
+        if self.adaptive:                                  # get_sakura_tstep
+            self.force("tstep_kernel", ("_tstep", "tstepij"), (self.eta,))
+            dmin = self.reduce(RED_SAKURA_DT, ("_tstep", "tstepij"), 0, self.eta)
+            self.L.step_begin(self.ctl, dmin)
+        else:
+            self._begin()
+        tau = self._tau_host()      # the pair kernel takes dt by value: one 8-byte read-back per step
+        if tau == 0.0:
+            return
+        r, v = st.need(*R3), st.need(*V3)
+        drv = st.need("drx", "dry", "drz", "dvx", "dvy", "dvz")
+        L.axpy(st.n, r, v, 0.5, 1.0, self.ctl)
+        for flag in (-1, 1):
+            self.force("sakura_kernel", ("drx", "dry", "drz", "dvx", "dvy", "dvz"), (tau / 2, flag))
+            L.axpy(st.n, r + v, drv)
+        L.axpy(st.n, r, v, 0.5, 1.0, self.ctl)
+        self._end()
+
+    # ---- NREG (integrator/nreg.py) -------------------------------------------------------------------
+    def _nreg_x(self, dt):
+        st, L = self.st, self.L
+        self.force("nreg_Xkernel", ("mrx", "mry", "mrz", "ax", "ay", "az", "u"), (dt,))
+        L.scale(st.n, st.need(*R3), st.need("mrx", "mry", "mrz"), self._nreg["mtot"])
+        u = self.reduce(RED_SUM, ("u",), 0)
+        self._nreg["U"] = 0.5 * self._real(u.item())
+        self._nreg["t"] = self._nreg["t"] + dt
+
+    def _nreg_v(self, dt):
+        st, L = self.st, self.L
+        self.force("nreg_Vkernel", ("mvx", "mvy", "mvz", "mk"), (dt,))
+        L.scale(st.n, st.need(*V3), st.need("mvx", "mvy", "mvz"), self._nreg["mtot"])
+        mk = self.reduce(RED_SUM, ("mk",), 0)
+        K = 0.25 * self._real(mk.item()) / self._nreg["mtot"]
+        self._nreg["W"] = K - self._nreg["E0"]
+
+    def _real(self, x):
+        # numpy's REAL scalar arithmetic of the reference (u.sum() is a REAL scalar)
+        return self.st.np_dtype.type(x)
+
+    def _anreg_step(self, h):
+        g = self._nreg
+        self._nreg_x(0.5 * (h / g["W"]))
+        self._nreg_v(h / g["U"])
+        self._nreg_x(0.5 * (h / g["W"]))
+
+    def _nreg_step(self):
+        st = self.st
+        if self._nreg is None:                             # NREG.initialize, nreg.py:110-131
+            ke, pe = self.energies()
+            self.reduce(RED_SUM, ("mass",), 0)
+            self._nreg = {"E0": ke + pe, "W": -pe, "U": -pe, "S": -pe, "mtot": float(self._scalar[0].item()),
+                          "t": self.time}
+        g = self._nreg
+        self._begin()
+        c = self.ctl.cpu()
+        if c[CTL_DONE] != 0:
+            return
+        tau = float(c[CTL_TAU])
+        t0 = g["t"]
+        if self.method == "anreg":
+            self._anreg_step(tau / 2)
+        else:                                              # nreg_step, nreg.py:87-94
+            self._anreg_step(0.5 * (tau * g["S"]))
+            g["S"] = 1 / (2 / g["W"] - 1 / g["S"])
+            self._anreg_step(0.5 * (tau * g["S"]))
+        dt = g["t"] - t0
+        # ps.tstep[...] = dt; ps.time += tau; ps.nstep += 1; the clock advanced by dt (nreg.py:159-166)
+        st["tstep"].fill_(float(dt))
+        st["time"].add_(tau)
+        st["nstep"].add_(1)
+        self.ctl[CTL_T_CURR] = float(g["t"])
+        self.ctl[CTL_NSTEPS] += 1
