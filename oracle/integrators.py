@@ -18,7 +18,7 @@ import sys
 
 import numpy as np
 
-from . import call, load
+from . import call, call_threaded, load
 
 S8 = ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz")
 S5 = ("mass", "rx", "ry", "rz", "eps2")
@@ -30,7 +30,8 @@ class Bodies(object):
     """SoA arrays + the class-level clock of the reference's ParticleSystem
     (particles/body.py:26-39; `type(ps).t_curr`, integrator/__init__.py:20)."""
 
-    def __init__(self, arrays, prec, kind="oracle"):
+    def __init__(self, arrays, prec, kind="oracle", threads=1):
+        self.threads = threads                    # > 1: contiguous i-slices in a thread pool
         self.prec = np.dtype(prec).name
         self.dtype = np.dtype(prec)
         self.lib = load(kind, self.prec)
@@ -85,7 +86,10 @@ class Bodies(object):
         jps.need(*[a for a in attrs if a not in jps.a])
         args = ([self.n] + [self.a[k] for k in attrs] + [jps.n] + [jps.a[k] for k in attrs]
                 + list(scalars) + [self.a[k] for k in outs])
-        call(self.lib, name, self.prec, *args)
+        if self.threads > 1:
+            call_threaded(self.lib, name, self.prec, self.threads, *args)
+        else:
+            call(self.lib, name, self.prec, *args)
 
     def set_phi(self, jps):
         self._call("phi_kernel", S5, jps, (), ("phi",))
@@ -444,9 +448,9 @@ def sakura_do_step(ps, method, eta, tau):        # Sakura.do_step + get_sakura_t
 
 
 # ---- driver (simulation.py:187-201 + Base.evolve_step, integrator/__init__.py:80-99) ---------------
-def evolve(arrays, prec, method, eta, t_end, kind="oracle", t0=0.0, max_steps=None):
+def evolve(arrays, prec, method, eta, t_end, kind="oracle", t0=0.0, max_steps=None, threads=1):
     """-> (Bodies after the run, number of steps)."""
-    ps = Bodies(arrays, prec, kind)
+    ps = Bodies(arrays, prec, kind, threads)
     ps.clock[0] = t0
     sia = SIA(method, eta) if method.startswith("sia") else None
     nreg = None

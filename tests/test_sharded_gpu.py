@@ -38,6 +38,26 @@ for n in (5000, 40001):
             # scale of the array, not per component (components cancel, SURVEY.md 7)
             err = np.max(np.abs(a - b)) / np.max(np.abs(b))
             assert err < 1e-12, (kernel, name, n, err)
+# the device-resident integrator, i-sharded (BASELINE.json configs[2] in miniature: Hermite6 with
+# the shared block step, acc_jerk + snap_crackle + tstep each with its own all-gather) against
+# the same integrator on one GPU
+from tupan_b200.integrator import Integrator
+for method, n in (("ahermite6", 3001), ("sia21a.kdk", 2500)):
+    a = Integrator(1.0 / 64, 0.0, ics.make_plummer(n, seed=3), method=method, device=dev)
+    b = Integrator(1.0 / 64, 0.0, ics.make_plummer(n, seed=3), method=method, device=dev, shard=False)
+    for it in (a, b):
+        for _ in range(4):
+            it.evolve_step(1.0)
+    assert a.world == world and b.world == 1
+    assert a.time == b.time and a.nsteps == b.nsteps == 4, (a.time, b.time)
+    pa, pb = a.particle_system, b.particle_system
+    lo, hi = a.st.lo, a.st.hi
+    for k in ("rx", "ry", "rz", "vx", "vy", "vz"):
+        x, y = getattr(pa, k)[lo:hi], getattr(pb, k)[lo:hi]
+        err = np.max(np.abs(x - y)) / np.max(np.abs(y))
+        assert err < 1e-12, (method, k, err)
+    ea, eb = a.energies(), b.energies()
+    assert abs(ea[0] - eb[0]) < 1e-12 and abs(ea[1] - eb[1]) < 1e-12, (ea, eb)
 dist.barrier()
 if rank == 0:
     print("SHARDED-GPU-OK world=%%d" %% world)

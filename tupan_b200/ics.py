@@ -70,3 +70,48 @@ def make_uniform(n, seed=0, dtype=np.float64, eps2=0.0):
     for name in ("rx", "ry", "rz", "vx", "vy", "vz"):
         getattr(ps, name)[...] = rng.random(n) * 10
     return ps if np.dtype(dtype) == np.float64 else ps.astype(dtype)
+
+
+def make_binary_rich(n, relative_size=1.0e-3, m_ratio=1.0, ecc=0.5, seed=1, dtype=np.float64, eps2=0.0,
+                     orient="random"):
+    """Binary-rich Plummer sphere (BASELINE.json configs[4]): every star of an n/2-body Plummer
+    model is replaced by a binary of the same total mass whose radius of gyration is
+    ``relative_size`` times the parent's -- what the reference builds with
+    ``make_hierarchy(make_plummer(n/2, ...), relative_size, make_binary, m1, m2, a, e)``
+    (``tupan/ics/hierarchy.py:12-29``, ``ics/fewbody.py:13-50``), vectorised.  Binaries start
+    at apocentre.  ``orient="reference"`` keeps the reference's layout (separation along x,
+    velocities along y for every binary); ``"random"`` draws an isotropic orientation per
+    binary.  Pair b is particles (2b, 2b+1).  Default ``eps2 = 0``: with softening, tight
+    binaries drive the reference's Kepler energy check into unbounded sub-stepping
+    (DESIGN.md, Sakura / Kepler)."""
+    nb = max(int(n) // 2, 1)
+    parent = make_plummer(nb, seed=seed)
+    rng = np.random.default_rng(seed + 7919)
+    M = parent.mass
+    m1 = M * m_ratio / (1.0 + m_ratio)
+    m2 = M - m1
+    # radius of gyration of the parent (particles/body.py:387-402)
+    rr = parent.rx ** 2 + parent.ry ** 2 + parent.rz ** 2
+    size = relative_size * np.sqrt(np.sum(M * rr) / np.sum(M))
+    # a binary at apocentre with separation d has gyration radius d sqrt(m1 m2)/M
+    d = size * M / np.sqrt(m1 * m2)
+    a = d / (1.0 + ecc)
+    v = np.sqrt(M / a * (1.0 - ecc) / (1.0 + ecc))
+    if orient == "reference":
+        ex = np.stack([np.ones(nb), np.zeros(nb), np.zeros(nb)])
+        ey = np.stack([np.zeros(nb), np.ones(nb), np.zeros(nb)])
+    else:
+        ex = np.stack(_unit_vectors(rng, nb))
+        t = np.stack(_unit_vectors(rng, nb))
+        ey = np.cross(ex.T, t.T).T
+        ey /= np.sqrt((ey ** 2).sum(0))
+    ps = ParticleSystem(2 * nb, np.float64)
+    f1, f2 = m2 / M, -m1 / M
+    for k, (mk, f) in enumerate(((m1, f1), (m2, f2))):
+        ps.mass[k::2] = mk
+        for c, name in enumerate(("rx", "ry", "rz")):
+            getattr(ps, name)[k::2] = getattr(parent, name) + f * d * ex[c]
+        for c, name in enumerate(("vx", "vy", "vz")):
+            getattr(ps, name)[k::2] = getattr(parent, name) + f * v * ey[c]
+    ps.eps2[...] = eps2
+    return ps if np.dtype(dtype) == np.float64 else ps.astype(dtype)

@@ -177,7 +177,8 @@ class Integrator(object):
                         + ["%s%s.%s" % (s, k, o) for s in sorted(SIA_COEFS) for k in "sa" for o in ("dkd", "kdk")]
                         + ["nreg", "anreg", "sakura", "asakura"])
 
-    def __init__(self, eta, time, ps, method=None, device=None, group=None, pn_order=0, clight=None, **kwargs):
+    def __init__(self, eta, time, ps, method=None, device=None, group=None, shard=None, pn_order=0,
+                 clight=None, **kwargs):
         if method not in self.PROVIDED_METHODS:
             if method and method.startswith("sia") and "h." in method:
                 raise NotImplementedError("hierarchical SIA splitting (%s) is not device-resident yet" % method)
@@ -192,7 +193,10 @@ class Integrator(object):
             raise TypeError("Integrator.__init__ received unexpected keyword arguments: %s." % ", ".join(kwargs))
         self.eta, self.method, self.ps = float(eta), method, ps
         self.group = group
-        self.world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
+        # shard=None: i-shard over the ranks of `group` whenever torch.distributed is initialised
+        if shard is None:
+            shard = dist.is_initialized()
+        self.world = dist.get_world_size(group) if shard else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
