@@ -203,6 +203,9 @@ void tupan_cuda_set_timing(int enable);
  * a device-resident call has no h2d/d2h stage and reports 0 for them) */
 void tupan_cuda_last_times(float *h2d, float *pack, float *pair, float *finalize, float *d2h);
 long long tupan_cuda_launch_count(void);           /* kernels launched since load */
+/* kernels of this library replayed from a CUDA graph the caller captured (launches inside a
+ * capture are counted once, at capture time; the caller adds them per replay) */
+void tupan_cuda_count_launches(long long n);
 int tupan_cuda_sm_count(void);
 /* FMA-pipe micro-benchmark in the library's precision: sustained TFLOP/s over `ms` ms */
 int tupan_cuda_fma_peak(double ms, double *tflops, double *sm_mhz_effective);
@@ -256,6 +259,10 @@ int tupan_cuda_scale_dev(int narr, long long n, void *const *y, const void *cons
  * sakura.py:136-139).  Array pointers may be NULL. */
 int tupan_cuda_step_end_dev(long long n, void *d_time, void *d_nstep, void *d_tstep, void *d_ctl,
                             void *stream);
+
+/* the same bookkeeping with the step given by the host (sub-systems of the hierarchical SIA
+ * recursion, sia.py:1108-1113): tstep[:] = tau; time += tau; nstep += 1 */
+int tupan_cuda_stamp_dev(long long n, void *d_time, void *d_nstep, void *d_tstep, double tau, void *stream);
 
 /* deterministic reductions over particles; the result is ONE double written to d_out */
 enum tupan_reduction {

@@ -45,6 +45,9 @@ _PREC = {
                     np=np.float64, tag="fp64"),
     "float32": dict(real=ctypes.c_float, uint=ctypes.c_uint, int=ctypes.c_int,
                     np=np.float32, tag="fp32"),
+    # x87 extended precision (numpy longdouble): the "truth" build of the restatement, oracle only
+    "float128": dict(real=ctypes.c_longdouble, uint=ctypes.c_ulong, int=ctypes.c_long,
+                     np=np.longdouble, tag="fp80"),
 }
 
 

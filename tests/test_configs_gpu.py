@@ -86,14 +86,18 @@ def test_config3_hermite6_n262144_one_step():
     sample14 = {k: np.ascontiguousarray(v[idx]) for k, v in full14.items()}
     ref = run(olib, "snap_crackle_kernel", "float64", sample14, full14)
     got = [st[k][idx] for k in ("sx", "sy", "sz", "cx", "cy", "cz")]
-    # At this N the crackle of some particles is a sum of 262144 terms that cancel to ~1e-5 of
-    # their magnitude, and the reference's own sequential sum is no longer good to 1e-12: the
-    # same C function with the j-set in reverse order moves it by `floor`.  The stated 1e-12
-    # holds wherever the reference itself is that well defined.
-    rev = {k: np.ascontiguousarray(v[::-1]) for k, v in full14.items()}
-    floor = rel_err("snap_crackle_kernel", run(olib, "snap_crackle_kernel", "float64", sample14, rev), ref)
+    # At this N the crackle of a particle with a close neighbour is a badly conditioned
+    # expression (jx - alpha ax - beta vx - gamma rx cancels to a small part of its terms), and
+    # two fp64 evaluations that round differently (the reference's C, ours with FMAs) differ by
+    # more than 1e-12 there.  Where the stated tolerance is exceeded, the x87 extended-precision
+    # build of the restatement decides: our error against it must not exceed 1.5x the
+    # reference's own (the criterion test_parity_gpu.py already uses for fp32).
     e = rel_err("snap_crackle_kernel", got, ref)
-    assert e <= max(1e-12, 2.0 * floor), (e, floor)
+    if e > 1e-12:
+        ld = lambda d: {k: v.astype(np.longdouble) for k, v in d.items()}
+        truth = run(oracle.load("oracle", "float128"), "snap_crackle_kernel", "float128", ld(sample14), ld(full14))
+        e_cuda, e_ref = rel_err("snap_crackle_kernel", got, truth), rel_err("snap_crackle_kernel", ref, truth)
+        assert e_cuda <= 1.5 * e_ref, (e, e_cuda, e_ref)
     # one full adaptive step: block step = the reference's quantisation of the GPU's min tstep
     it.evolve_step(1.0)
     tau = oi.get_min_block_tstep(np.abs(st["_tstep"]).min(), 0.0, oi.get_base_tstep(0.0, 1.0, eta))

@@ -17,12 +17,13 @@ def test_operator_sequences_match_the_pinned_restatement():
 
 def test_method_names_are_the_reference_ones():
     # integrator/hermite.py:291-295, sia.py:969-985, nreg.py:103-104, sakura.py:58-59
-    for m in ("hermite2", "ahermite8", "sia21s.dkd", "sia69a.kdk", "nreg", "anreg", "sakura", "asakura"):
+    for m in ("hermite2", "ahermite8", "sia21s.dkd", "sia69a.kdk", "sia43h.kdk", "nreg", "anreg", "sakura",
+              "asakura"):
         assert m in Integrator.PROVIDED_METHODS
     with pytest.raises(ValueError):
         Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="rk4", device="cpu")
     with pytest.raises(NotImplementedError):
-        Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="sia21h.dkd", device="cpu")
+        Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="sia21s.dkd", device="cpu", pn_order=7, clight=128)
 
 
 def test_no_cpu_fallback():

@@ -2,9 +2,9 @@
 one JSON line: steps, energies, relative energy error (te - te0)/(-pe) (the reference's
 Diagnostic, simulation.py:109-112), wall time, steps/s and pair-interactions/s.
 
-    python tools/run_integration.py --n 1024 --method ahermite4 --eta 0.015625 --t-end 1
-    python tools/run_integration.py --n 65536 --method sia21s.dkd --eta 0.00390625 --t-end 0.015625 --prec float32
-    torchrun ... tools/run_integration.py --n 262144 --method ahermite6 --max-steps 4      # i-sharded
+    python tools/run_integration.py n=1024 method=ahermite4 eta=0.015625 t_end=1
+    python tools/run_integration.py n=65536 method=sia21s.dkd eta=0.00390625 t_end=0.015625 prec=float32
+    torchrun ... tools/run_integration.py n=262144 method=ahermite6 max_steps=4      # i-sharded
 """
 import argparse
 import json
@@ -40,16 +40,17 @@ def evals_per_step(method):
 
 
 def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1024)
-    ap.add_argument("--method", default="ahermite4")
-    ap.add_argument("--eta", type=float, default=1.0 / 64)
-    ap.add_argument("--t-end", type=float, default=1.0)
-    ap.add_argument("--prec", default="float64")
-    ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--max-steps", type=int, default=None)
-    ap.add_argument("--check-every", type=int, default=16)
-    args = ap.parse_args()
+    # key=value tokens on purpose: torchrun's own parser abbreviation-matches long options that
+    # follow the script name (--n -> --nnodes ...)
+    opts = {"n": 1024, "method": "ahermite4", "eta": 1.0 / 64, "t_end": 1.0, "prec": "float64", "seed": 1,
+            "max_steps": None, "check_every": 16, "graph": None}
+    for tok in sys.argv[1:]:
+        k, v = tok.split("=", 1)
+        if k not in opts:
+            raise SystemExit("unknown option %r (known: %s)" % (k, ", ".join(sorted(opts))))
+        opts[k] = v if k in ("method", "prec") else (int(v) if k in ("n", "seed", "max_steps", "check_every", "graph")
+                                                     else float(v))
+    args = argparse.Namespace(**opts)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -59,7 +60,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = backend.require_gpu(args.prec)
     ps = ics.make_plummer(args.n, seed=args.seed, dtype=args.prec)
-    it = Integrator(args.eta, 0.0, ps, method=args.method, device=dev)
+    it = Integrator(args.eta, 0.0, ps, method=args.method, device=dev,
+                    graph=None if args.graph is None else bool(args.graph))
     ke0, pe0 = it.energies()
     it.evolve_step(args.t_end)                   # warm-up step: buffers sized, kernels loaded
     torch.cuda.synchronize()
@@ -81,7 +83,7 @@ def main():
             "steps_per_s": timed / wall, "us_per_step": 1e6 * wall / max(timed, 1),
             "pair_kernel_evals_per_step": per,
             "pairs_per_s": per * float(args.n) ** 2 * timed / wall,
-            "gpu_launches_per_step": launches / max(timed, 1)}), flush=True)
+            "gpu_launches_per_step": launches / max(timed, 1), "cuda_graph": it._graph is not None}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

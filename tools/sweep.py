@@ -1,6 +1,6 @@
 """BASELINE.json configs[3]: acc_jerk fp64 throughput sweep, N = 2^14 ... 2^22, on 1/2/4/8 GPUs.
 
-    python tools/sweep.py [--min 14] [--max 22] [--prec float64] [--kernel acc_jerk_kernel]
+    python tools/sweep.py [lo=14] [hi=22] [prec=float64] [kernel=acc_jerk_kernel]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 \
         --master-port 29577 tools/sweep.py ...
 
@@ -26,10 +26,12 @@ FLOPS = {"phi_kernel": 14, "acc_kernel": 20, "acc_jerk_kernel": 42, "snap_crackl
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--min", type=int, default=14)
-    ap.add_argument("--max", type=int, default=22)
-    ap.add_argument("--prec", default="float64")
-    ap.add_argument("--kernel", default="acc_jerk_kernel")
+    # positional on purpose: torchrun's own parser abbreviates-matches long options that follow
+    # the script name (--lo -> --log-dir ...)
+    ap.add_argument("lo", type=int, nargs="?", default=14)
+    ap.add_argument("hi", type=int, nargs="?", default=22)
+    ap.add_argument("prec", nargs="?", default="float64")
+    ap.add_argument("kernel", nargs="?", default="acc_jerk_kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -46,7 +48,7 @@ def main():
         print("# %s %s on %d x %s; FMA-pipe peak measured in-process: %.2f TFLOP/s per GPU (%.0f MHz effective)"
               % (args.kernel, args.prec, world, torch.cuda.get_device_name(dev), peak, mhz))
         print("# %8s %10s %12s %10s %8s %8s" % ("N", "ms", "Gpair/s", "TFLOP/s", "%peak", "per-GPU"))
-    for p in range(args.min, args.max + 1):
+    for p in range(args.lo, args.hi + 1):
         n = 1 << p
         ps = ics.make_plummer(n, seed=1, dtype=args.prec)
         full = device.to_device(ps, device=dev)

@@ -70,6 +70,7 @@ PART2 = {
     "tupan_cuda_set_timing": (None, [ctypes.c_int]),
     "tupan_cuda_last_times": (None, [ctypes.POINTER(ctypes.c_float)] * 5),
     "tupan_cuda_launch_count": (ctypes.c_longlong, []),
+    "tupan_cuda_count_launches": (None, [ctypes.c_longlong]),
     "tupan_cuda_sm_count": (ctypes.c_int, []),
     "tupan_cuda_fma_peak": (ctypes.c_int, [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
@@ -88,6 +89,8 @@ PART2 = {
                                             ctypes.c_double, ctypes.c_void_p]),
     "tupan_cuda_step_end_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_stamp_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_double, ctypes.c_void_p]),
     "tupan_cuda_reduce_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double,
                                              ctypes.c_void_p, ctypes.c_void_p]),
 }

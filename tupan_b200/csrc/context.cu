@@ -299,6 +299,7 @@ void tupan_cuda_last_times(float* h2d, float* pack, float* pair, float* fin, flo
     if (d2h) *d2h = c.last.d2h_ms;
 }
 long long tupan_cuda_launch_count(void) { return ctx().launches; }
+void tupan_cuda_count_launches(long long n) { ctx().launches += n; }
 int tupan_cuda_sm_count(void)
 {
     Context& c = ctx();

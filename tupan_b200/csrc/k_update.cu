@@ -219,6 +219,20 @@ __global__ void __launch_bounds__(256) step_end_kernel(long long n, real_t* __re
     if (nstep) nstep[i] = nstep[i] + 1;
 }
 
+// The same bookkeeping for a sub-system of the hierarchical SIA recursion, where the step of each
+// level is known on the host (sia.py:1108-1113: slow.tstep[...] = tau; slow.time += tau; ...)
+__global__ void __launch_bounds__(256) stamp_kernel(long long n, real_t* __restrict__ time,
+                                                    abi_uint* __restrict__ nstep, real_t* __restrict__ tstep,
+                                                    double tau)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const real_t t = (real_t)tau;
+    if (tstep) tstep[i] = t;
+    if (time) time[i] = time[i] + t;
+    if (nstep) nstep[i] = nstep[i] + 1;
+}
+
 // ---------------------------------------------------------------------------------------
 // Reductions over particles (deterministic: fixed grid, fixed tree; double accumulation).
 // ---------------------------------------------------------------------------------------
@@ -439,6 +453,20 @@ int tupan_cuda_step_end_dev(long long n, void* d_time, void* d_nstep, void* d_ts
     step_end_kernel<<<blocks_for(m), 256, 0, (cudaStream_t)stream>>>(n, (real_t*)d_time, (abi_uint*)d_nstep,
                                                                      (real_t*)d_tstep, (double*)d_ctl);
     TUPAN_CHECK(cudaGetLastError(), "step_end_kernel");
+    c->launches++;
+    return 0;
+}
+
+int tupan_cuda_stamp_dev(long long n, void* d_time, void* d_nstep, void* d_tstep, double tau, void* stream)
+{
+    Context* c;
+    std::lock_guard<std::mutex> lock(ctx().mu);
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if (n <= 0) return 0;
+    stamp_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(n, (real_t*)d_time, (abi_uint*)d_nstep,
+                                                                  (real_t*)d_tstep, tau);
+    TUPAN_CHECK(cudaGetLastError(), "stamp_kernel");
     c->launches++;
     return 0;
 }

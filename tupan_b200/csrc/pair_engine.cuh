@@ -283,10 +283,10 @@ inline int throughput_slots(const DeviceInfo& dev)
 
 // Launch shape.
 //   * throughput shape (WPT particles per thread, unrolled j loop) whenever the i-blocks times
-//     the j chunks available can fill every CTA slot of the chip; the number of j chunks is
-//     then chosen so that the CTA count is (nearly) a whole number of waves -- all CTAs do
-//     the same work, so a partial last wave is pure loss (N = 2^20 / 8 GPUs: 256 i-blocks on
-//     296 slots would idle 14 % of the chip; 37 chunks make it 32 full waves);
+//     the j chunks available can fill every CTA slot of the chip.  All CTAs of a wave run for as
+//     long as the longest of them, so the chunk length (in tiles) is chosen to minimise
+//     waves x (tiles per chunk + a fixed per-CTA cost): N = 2^20 on 8 GPUs has 256 i-blocks for
+//     296 slots -- one chunk would idle 14 % of the chip, 37 chunks of 28 tiles make 32 full waves;
 //   * lane split (several lanes per particle) for small ni.
 template <class Op>
 inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
@@ -297,17 +297,21 @@ inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
     const long long IB = (long long)U::NT * Op::WPT;
     const long long iblocks = (ni + IB - 1) / IB;
     const long long slots = throughput_slots<Op>(dev);
-    long long maxg = nj / (8 * TJ);               // a chunk is at least 8 tiles
+    const long long tiles = (nj + TJ - 1) / TJ;
+    const long long min_tiles = 2;                 // a chunk is at least 2 tiles (256 rows)
+    long long maxg = tiles / min_tiles;
     if (maxg > 64) maxg = 64;
     if (maxg < 1) maxg = 1;
     if (iblocks * maxg >= slots && ni * 10 >= iblocks * IB * 9) {
-        double best = 0.0;
+        double best = 1e300;
         for (long long g = 1; g <= maxg; ++g) {
-            const long long ctas = iblocks * g;
+            const long long tpc = (tiles + g - 1) / g;            // tiles per chunk
+            const long long chunks = (tiles + tpc - 1) / tpc;     // non-empty chunks
+            if (chunks != g) continue;                            // same split as a smaller g
+            const long long ctas = iblocks * chunks;
             const long long waves = (ctas + slots - 1) / slots;
-            const double eff = (double)ctas / (double)(waves * slots);
-            if (eff > best + 1e-9) { best = eff; p.jg = (int)g; }
-            if (eff >= 0.985) { p.jg = (int)g; break; }
+            const double cost = (double)waves * ((double)tpc + 0.5) + 0.02 * (double)g;
+            if (cost < best) { best = cost; p.jg = (int)g; }
         }
         return p;
     }

@@ -15,7 +15,10 @@ round trip.  ``.time`` / ``.particle_system`` synchronise and download.
 The O(N) updates follow the reference's operation order exactly, so the only numerical
 difference from the reference is the summation order inside the pair kernels.
 
-Not covered here (raises): hierarchical ``sia..h`` splitting and post-Newtonian kicks.
+The hierarchical ``sia..h`` methods split the system by time-step at every level
+(data-dependent sub-system sizes): their recursion is driven from the host like the
+reference's, with the sub-systems gathered on the device (torch indexing as plumbing) and
+rectangular ``acc`` calls between the slow and fast sets.  Post-Newtonian kicks raise.
 There is no CPU path: the CUDA library must be loadable and a GPU present.
 """
 import ctypes
@@ -112,7 +115,7 @@ class DeviceState(object):
                     continue
                 ps.register_auxiliary_attribute(k, "real")
             dst = getattr(ps, k)
-            if k == "nstep":
+            if k in ("nstep", "id"):
                 dst = dst.view(h.dtype)
             dst[self.lo:self.hi] = h
 
@@ -174,14 +177,12 @@ class _Lib(object):
 
 class Integrator(object):
     PROVIDED_METHODS = (["hermite%d" % o for o in (2, 4, 6, 8)] + ["ahermite%d" % o for o in (2, 4, 6, 8)]
-                        + ["%s%s.%s" % (s, k, o) for s in sorted(SIA_COEFS) for k in "sa" for o in ("dkd", "kdk")]
+                        + ["%s%s.%s" % (s, k, o) for s in sorted(SIA_COEFS) for k in "sah" for o in ("dkd", "kdk")]
                         + ["nreg", "anreg", "sakura", "asakura"])
 
-    def __init__(self, eta, time, ps, method=None, device=None, group=None, shard=None, pn_order=0,
+    def __init__(self, eta, time, ps, method=None, device=None, group=None, shard=None, graph=None, pn_order=0,
                  clight=None, **kwargs):
         if method not in self.PROVIDED_METHODS:
-            if method and method.startswith("sia") and "h." in method:
-                raise NotImplementedError("hierarchical SIA splitting (%s) is not device-resident yet" % method)
             raise ValueError("Unexpected integration method: %r. Provided methods: %s"
                              % (method, self.PROVIDED_METHODS))
         if pn_order:
@@ -213,6 +214,14 @@ class Integrator(object):
         self._scalar = torch.zeros(4, dtype=torch.float64, device=self.device)
         self._sharded = {}
         self.is_initialized = False
+        # A Hermite / SIA step is a fixed sequence of launches whose only step-dependent input
+        # (tau) lives in device memory: after two eager steps it is captured once into a CUDA
+        # graph and replayed -- small-N steps are launch-bound otherwise (19 launches per
+        # ahermite4 step).  Not for the sharded path (collectives on a second stream) nor for
+        # sakura / nreg (they read a scalar back every step).
+        capturable = self.world == 1 and ("hermite" in method or (method.startswith("sia") and method[5] != "h"))
+        self.use_graph = capturable if graph is None else (bool(graph) and capturable)
+        self._graph, self._graph_kernels, self._eager = None, 0, 0
         self.adaptive = method.startswith("a") or (method.startswith("sia") and method[5] == "a")
         if "hermite" in method:
             self.order = int(method[-1])
@@ -221,6 +230,13 @@ class Integrator(object):
             self._step = self._sia_step
             A, B = SIA_COEFS[method[:5]]
             kdk = method.endswith("kdk")
+            self._kdk = kdk
+            if method[5] == "h":
+                if self.world > 1:
+                    raise NotImplementedError("hierarchical SIA is single-GPU")
+                self._step = self._sia_h_step
+                self.st.t["id"] = self.st._up(np.ascontiguousarray(ps.id).view(
+                    np.int64 if self.st.np_dtype == np.float64 else np.int32))
             # bridge_sf with an empty fast set (sia.py:341-352): only the sf_drifts act, each
             # one evolve(slow, B_i * tau); evolve = the dkd / kdk composition (sia.py:308-337)
             self._bridge = [w for outer, w in operator_sequence(B, A) if outer]
@@ -286,9 +302,27 @@ class Integrator(object):
         if not self.is_initialized:
             self.initialize(t_end)
         self._set_t_end(t_end)
-        self._step()
+        if self._graph is not None:
+            self._graph.replay()
+            self.L.lib.tupan_cuda_count_launches(self._graph_kernels)
+        else:
+            self._step()
+            self._eager += 1
+            if self.use_graph and self._eager == 2:
+                self._capture()
         if self.reporter:
             self.reporter.diagnostic_report(self.particle_system)
+
+    def _capture(self):
+        lib = self.L.lib
+        torch.cuda.synchronize(self.device)
+        before = lib.tupan_cuda_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()                       # recorded, not executed
+        self._graph_kernels = lib.tupan_cuda_launch_count() - before
+        lib.tupan_cuda_count_launches(-self._graph_kernels)
+        self._graph = g
 
     def evolve(self, t_end, check_every=8, max_steps=None):
         """The driver loop `while abs(time) < t_end: evolve_step(t_end)` (simulation.py:187-201)
@@ -386,6 +420,102 @@ class Integrator(object):
                     self.force("acc_kernel", A3)           # kick = set_acc + kick_n
                     L.axpy(st.n, v, a, wb, w, self.ctl)
         self._end()
+
+    # ---- SIA, hierarchical (individual block steps by recursive slow/fast splitting) ----------------
+    # Mirrors SIA.recurse / split / join / sf_drift / sf_kick (sia.py:25-58, 192-294, 1089-1123).
+    # A sub-system is a dict of device tensors; forces between sub-systems are rectangular
+    # acc calls (ni != nj).  The recursion, like the reference's, is host logic: the size of
+    # the slow and fast sets is data the host has to see.
+    def _sub_force(self, kernel, ips, jps, out_names, scalars=()):
+        for k in out_names:
+            if k not in ips:
+                ips[k] = torch.zeros_like(ips["mass"])
+        src_i = {a: ips[a] for a in KERNEL_INPUTS[kernel]}
+        src_j = {a: jps[a] for a in KERNEL_INPUTS[kernel]}
+        run_kernel(kernel, src_i, src_j, scalars, dict(zip(KERNEL_OUTPUTS[kernel], [ips[k] for k in out_names])))
+
+    @staticmethod
+    def _sub_n(sub):
+        return sub["mass"].numel()
+
+    def _sub_axpy(self, sub, y, x, dt):
+        self.L.axpy(self._sub_n(sub), [sub[k] for k in y], [sub[k] for k in x], dt, 1.0, None)
+
+    def _sub_evolve(self, sub, tau):
+        """SIAxy.dkd / .kdk on one sub-system (sia.py:308-337); n <= 2 -> FewBody.evolve."""
+        n = self._sub_n(sub)
+        if n == 0:
+            return sub
+        if n == 1:                                         # fewbody.py:18-27
+            self._sub_axpy(sub, R3, V3, tau)
+            return sub
+        if n == 2:                                         # kepler_solver, in place (fewbody.py:34-44)
+            ins = [sub[k] for k in ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz")]
+            outs = [sub[k] for k in R3 + V3]
+            self.L.ok(self.L.lib.tupan_cuda_kepler_dev(1, self.L.ptrs(ins), tau, self.L.ptrs(outs), self.L.stream()),
+                      "kepler")
+            return sub
+        for is_drift, w in self._evolve:
+            if is_drift:
+                self._sub_axpy(sub, R3, V3, w * tau)
+            else:
+                self._sub_force("acc_kernel", sub, sub, A3)
+                self._sub_axpy(sub, V3, A3, w * tau)
+        return sub
+
+    def _sub_recurse(self, sub, tau):
+        n = self._sub_n(sub)
+        if n == 0:
+            return sub
+        self._sub_force("tstep_kernel", sub, sub, ("tstep", "tstepij"), (self.eta,))
+        if n <= 2:                                         # split(): stop the recursion
+            slow, fast = sub, {k: v[:0] for k, v in sub.items()}
+        else:
+            cond = sub["tstep"].abs() > abs(tau)
+            slow = {k: v[cond].contiguous() for k, v in sub.items()}
+            ncond = ~cond
+            fast = {k: v[ncond].contiguous() for k, v in sub.items()}
+        A, B = SIA_COEFS[self.method[:5]]
+        for outer, w in operator_sequence(B, A):           # bridge_sf, e.g. sia.py:341-352
+            if outer:                                      # sf_drift
+                slow = self._sub_evolve(slow, w * tau)
+                fast = self._sub_recurse(fast, w * tau)
+            elif self._sub_n(slow) and self._sub_n(fast):  # sf_kick
+                self._sub_force("acc_kernel", slow, fast, A3)
+                self._sub_force("acc_kernel", fast, slow, A3)
+                self._sub_axpy(slow, V3, A3, w * tau)
+                self._sub_axpy(fast, V3, A3, w * tau)
+        if self._sub_n(fast) == 0:
+            self._h_t += tau
+        ns = self._sub_n(slow)
+        if ns:
+            self.L.ok(self.L.lib.tupan_cuda_stamp_dev(ns, slow["time"].data_ptr(), slow["nstep"].data_ptr(),
+                                                      slow["tstep"].data_ptr(), tau, self.L.stream()), "stamp")
+        if not self._sub_n(fast):                          # join()
+            return slow
+        if not ns:
+            return fast
+        for k in set(slow) | set(fast):
+            if k not in slow:
+                slow[k] = torch.zeros_like(slow["mass"])
+            if k not in fast:
+                fast[k] = torch.zeros_like(fast["mass"])
+        return {k: torch.cat([slow[k], fast[k]]) for k in slow}
+
+    def _sia_h_step(self):
+        c = self.ctl.cpu()
+        self._h_t = float(c[CTL_T_CURR])
+        t_end = float(c[CTL_T_END])
+        if not (abs(self._h_t) < abs(t_end)):
+            return
+        # Base.get_base_tstep, integrator/__init__.py:48-57
+        dt = min(abs(t_end) - abs(self._h_t), abs(self.eta))
+        dt = max(dt, abs(t_end) * (2 * np.finfo(np.float64).eps))
+        tau = float(np.copysign(dt, self.eta))
+        sub = {k: v for k, v in self.st.t.items() if not (k.endswith("0") or k.startswith("_"))}
+        self.st.t = self._sub_recurse(sub, tau)
+        self.ctl[CTL_T_CURR] = self._h_t
+        self.ctl[CTL_NSTEPS] += 1
 
     # ---- Sakura (integrator/sakura.py:22-50, 100-147) -------------------------------------------
     def _tau_host(self):

@@ -84,6 +84,8 @@ class ShardedKernel(object):
     of the reference's particle arrays) and returns the kernel outputs for that shard.
     """
 
+    OVERLAP_MIN_PAIRS = 2.0e9      # ~4 ms of acc_jerk fp64 on a B200
+
     def __init__(self, kernel, n_total, dtype=torch.float64, device="cuda", group=None, engine=None,
                  overlap=True):
         self.kernel = kernel
@@ -105,16 +107,17 @@ class ShardedKernel(object):
         self._width = None
 
     # rows of rank r live at [r * rows_max, r * rows_max + count_r) of the gathered buffer
-    def segments(self):
+    def segments(self, split_local=True):
         """Contiguous row ranges of the gathered buffer: [(j0, j1, is_local)], adjacent full
-        shards merged so that equal shards give at most three sweeps."""
+        shards merged so that equal shards give at most three sweeps (one when the local rows
+        are not swept separately)."""
         segs = []
         for r in range(self.world):
             cnt = self.bounds[r + 1] - self.bounds[r]
             if cnt == 0:
                 continue
             j0 = r * self.rows_max
-            local = r == self.rank
+            local = split_local and r == self.rank
             if segs and not local and not segs[-1][2] and segs[-1][1] == j0:
                 segs[-1] = (segs[-1][0], j0 + cnt, False)
             else:
@@ -143,19 +146,23 @@ class ShardedKernel(object):
         mine = packed[self.rank * chunk:(self.rank + 1) * chunk]
         eng.pack(self.kernel, it, scalars, mine)
 
+        # Sweeping the local rows while the remote ones are in flight hides the all-gather (tens
+        # of microseconds) at the price of one more launch and a smaller, less evenly filled
+        # grid per sweep: worth it only when the local sweep is long.
+        overlap = self.overlap and float(ni) * (self.hi - self.lo) >= self.OVERLAP_MIN_PAIRS
         work = None
         if self.world > 1:
             if not self.on_cuda:
                 # gloo (CPU tests): no in-place aliasing of input and output
                 dist.all_gather_into_tensor(packed, mine.clone(), group=self.group)
-            elif self.overlap:
+            elif overlap:
                 self.comm_stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self.comm_stream):
                     work = dist.all_gather_into_tensor(packed, mine, group=self.group, async_op=True)
             else:
                 dist.all_gather_into_tensor(packed, mine, group=self.group)
 
-        segs = self.segments()
+        segs = self.segments(split_local=overlap or not self.on_cuda)
         segs.sort(key=lambda s: not s[2])            # local rows first: they need no communication
         nslots = [eng.sweep_slots(self.kernel, ni, j1 - j0, scalars) for (j0, j1, _) in segs]
         na = eng.n_acc(self.kernel, scalars)
