@@ -22,6 +22,7 @@ rectangular ``acc`` calls between the slow and fast sets.  Post-Newtonian kicks 
 There is no CPU path: the CUDA library must be loadable and a GPU present.
 """
 import ctypes
+import gc
 
 import numpy as np
 import torch
@@ -225,16 +226,16 @@ class Integrator(object):
         self.adaptive = method.startswith("a") or (method.startswith("sia") and method[5] == "a")
         if "hermite" in method:
             self.order = int(method[-1])
-            self._step = self._hermite_step
+            self._step_name = "_hermite_step"
         elif method.startswith("sia"):
-            self._step = self._sia_step
+            self._step_name = "_sia_step"
             A, B = SIA_COEFS[method[:5]]
             kdk = method.endswith("kdk")
             self._kdk = kdk
             if method[5] == "h":
                 if self.world > 1:
                     raise NotImplementedError("hierarchical SIA is single-GPU")
-                self._step = self._sia_h_step
+                self._step_name = "_sia_h_step"
                 self.st.t["id"] = self.st._up(np.ascontiguousarray(ps.id).view(
                     np.int64 if self.st.np_dtype == np.float64 else np.int32))
             # bridge_sf with an empty fast set (sia.py:341-352): only the sf_drifts act, each
@@ -242,9 +243,9 @@ class Integrator(object):
             self._bridge = [w for outer, w in operator_sequence(B, A) if outer]
             self._evolve = [(outer != kdk, w) for outer, w in operator_sequence(B, A)]   # (is_drift, weight)
         elif "sakura" in method:
-            self._step = self._sakura_step
+            self._step_name = "_sakura_step"
         else:
-            self._step = self._nreg_step
+            self._step_name = "_nreg_step"
             self._nreg = None
 
     # ---- forces --------------------------------------------------------------------------
@@ -313,16 +314,30 @@ class Integrator(object):
         if self.reporter:
             self.reporter.diagnostic_report(self.particle_system)
 
+    def _step(self):
+        # looked up by name: a bound method stored on self would be a reference cycle, and the
+        # cyclic GC would then destroy this object's CUDA graph at an arbitrary moment
+        getattr(self, self._step_name)()
+
     def _capture(self):
         lib = self.L.lib
         torch.cuda.synchronize(self.device)
-        before = lib.tupan_cuda_launch_count()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._step()                       # recorded, not executed
-        self._graph_kernels = lib.tupan_cuda_launch_count() - before
-        lib.tupan_cuda_count_launches(-self._graph_kernels)
-        self._graph = g
+        # destroying another CUDA graph (or freeing device memory) while this stream captures
+        # invalidates the capture: collect garbage now, and keep the collector off meanwhile
+        gc.collect()
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            before = lib.tupan_cuda_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step()                   # recorded, not executed
+            self._graph_kernels = lib.tupan_cuda_launch_count() - before
+            lib.tupan_cuda_count_launches(-self._graph_kernels)
+            self._graph = g
+        finally:
+            if was_enabled:
+                gc.enable()
 
     def evolve(self, t_end, check_every=8, max_steps=None):
         """The driver loop `while abs(time) < t_end: evolve_step(t_end)` (simulation.py:187-201)
