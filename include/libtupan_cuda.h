@@ -272,7 +272,10 @@ enum tupan_reduction {
     TUPAN_RED_SAKURA_DT = 3, /* eta / sqrt(1 + max((eta/x0)^2-(eta/x1)^2)), param = eta
                                 (tstep, tstepij)                      (sakura.py:100-110)        */
     TUPAN_RED_ABS_MIN = 4,   /* min |x0|                              (body.py:364-368)          */
-    TUPAN_RED_ABS_MAX = 5    /* max |x0|                              (body.py:370-374)          */
+    TUPAN_RED_ABS_MAX = 5,   /* max |x0|                              (body.py:370-374)          */
+    TUPAN_RED_DOT = 6,       /* sum x0 x1  (m r, m v: centre of mass, linear momentum; body.py:88-126) */
+    TUPAN_RED_MOMENT = 7     /* sum x0 (x1 x4 - x2 x3)  (m, ra, rb, va, vb: one component of the
+                                angular momentum, body.py:175-186)                               */
 };
 int tupan_cuda_reduce_dev(int what, long long n, const void *const *arrays, double param, void *d_out,
                           void *stream);

@@ -123,3 +123,20 @@ def test_steps_past_t_end_are_noops():
     assert it.nsteps == n0 and it.time == 1.0 / 32
     for k, v in before.items():
         assert np.array_equal(getattr(after, k), v), k
+
+
+def test_device_diagnostics_match_numpy():
+    """Energies, centre of mass, linear and angular momentum (the reference's Diagnostic report,
+    simulation.py:75-129; particles/body.py:60-306) reduced on the device."""
+    ps = ics.make_plummer(5000, seed=8)
+    ps.vx += 0.25                                           # give the system net momentum
+    it = Integrator(1.0 / 64, 0.0, ps, method="hermite4")
+    d = it.diagnostics()
+    m, r, v = ps.mass, np.stack([ps.rx, ps.ry, ps.rz]), np.stack([ps.vx, ps.vy, ps.vz])
+    assert d["ke"] == pytest.approx(0.5 * np.sum(m * (v ** 2).sum(0)), rel=1e-13)
+    assert d["mtot"] == pytest.approx(m.sum(), rel=1e-14)
+    assert np.allclose(d["com_r"], (m * r).sum(1) / m.sum(), rtol=0, atol=1e-15)
+    assert np.allclose(d["lmom"], (m * v).sum(1), rtol=1e-13)
+    assert np.allclose(d["amom"], (m * np.cross(r.T, v.T).T).sum(1), rtol=1e-12, atol=1e-15)
+    ke, pe = it.energies()
+    assert d["pe"] == pe and d["virial"] == pytest.approx(2 * ke + pe, rel=1e-14)

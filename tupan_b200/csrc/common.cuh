@@ -61,8 +61,8 @@ constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
 //                  absorbed by the cubic step); a masked r1 is a denormal ~1e-314 whose square
 //                  underflows to exactly 0 -- for kernels that use r1 only through r1^2, r1^3.
 //
-// fp32: MUFU.RSQ (rsqrt.approx.ftz.f32, max rel. error 2^-22.4), select on r2 > 0, one Newton
-// step  y = y0 * (k0 + k1*h).
+// fp32: MUFU.RSQ (rsqrt.approx.ftz.f32, max rel. error 2^-22.4), select on r2 > 0, scaled by k0;
+// no refinement (see below; -DTUPAN_FP32_NEWTON restores one Newton step y0 * (k0 + k1*h)).
 // ---------------------------------------------------------------------------------------
 template <bool CLEAN>
 TUPAN_DEV double rsqrt_seed_masked(double x, double r2)
@@ -117,8 +117,17 @@ TUPAN_DEV float rsqrt_scaled(float x, float r2, float k0, float k1, float)
     float y0;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
     y0 = (r2 > 0.0f) ? y0 : 0.0f;
+#ifdef TUPAN_FP32_NEWTON
     const float h = fmaf(-x * y0, y0, 1.0f);
     return y0 * fmaf(h, k1, k0);
+#else
+    // MUFU.RSQ is good to 2^-22.4 (1.5 ulp); the fp32 kernels are issue-bound (31 FP32 + 4 other
+    // instructions per pair, tools/microbench_fp32.cu) and a Newton step costs 3-4 of them for
+    // half an ulp per pair, far below the rounding of the j sum itself.  north_star asks for the
+    // refinement on the fp64 paths only.
+    (void)k1;
+    return y0 * k0;
+#endif
 }
 
 template <typename T> struct InvR { T r1, r2, r3; };

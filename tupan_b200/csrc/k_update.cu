@@ -236,15 +236,16 @@ __global__ void __launch_bounds__(256) stamp_kernel(long long n, real_t* __restr
 // ---------------------------------------------------------------------------------------
 // Reductions over particles (deterministic: fixed grid, fixed tree; double accumulation).
 // ---------------------------------------------------------------------------------------
-enum { RED_SUM = 0, RED_KINETIC = 1, RED_HALF_DOT = 2, RED_SAKURA_DT = 3, RED_ABS_MIN = 4, RED_ABS_MAX = 5 };
+enum { RED_SUM = 0, RED_KINETIC = 1, RED_HALF_DOT = 2, RED_SAKURA_DT = 3, RED_ABS_MIN = 4, RED_ABS_MAX = 5,
+       RED_DOT = 6, RED_MOMENT = 7, RED_COUNT = 8 };
 
 struct RedRefs {
-    const real_t* x[4];
+    const real_t* x[5];
     long long n;
     double param;
 };
 
-TUPAN_DEV bool red_is_sum(int what) { return what <= RED_HALF_DOT; }
+TUPAN_DEV bool red_is_sum(int what) { return what <= RED_HALF_DOT || what >= RED_DOT; }
 
 TUPAN_DEV double red_term(int what, const RedRefs& a, long long i)
 {
@@ -260,6 +261,9 @@ TUPAN_DEV double red_term(int what, const RedRefs& a, long long i)
             const real_t wa = eta / a.x[0][i], wb = eta / a.x[1][i];
             return (double)(wa * wa - wb * wb);
         }
+        case RED_DOT: return (double)(a.x[0][i] * a.x[1][i]);        // m * r, m * v: body.py:60-72, 88-126
+        case RED_MOMENT:   // m (ra vb - rb va): one component of the angular momentum, body.py:175-186
+            return (double)(a.x[0][i] * (a.x[1][i] * a.x[4][i] - a.x[2][i] * a.x[3][i]));
         default: return fabs((double)a.x[0][i]);
     }
 }
@@ -477,10 +481,10 @@ int tupan_cuda_reduce_dev(int what, long long n, const void* const* arrays, doub
     std::lock_guard<std::mutex> lock(ctx().mu);
     int rc = begin_call(c);
     if (rc) return rc;
-    if (what < RED_SUM || what > RED_ABS_MAX) return c->fail(cudaErrorInvalidValue, "reduce: unknown reduction");
-    static const int nin[] = {1, 4, 2, 2, 1, 1};
+    if (what < RED_SUM || what >= RED_COUNT) return c->fail(cudaErrorInvalidValue, "reduce: unknown reduction");
+    static const int nin[] = {1, 4, 2, 2, 1, 1, 2, 5};
     RedRefs a;
-    for (int k = 0; k < 4; ++k) a.x[k] = k < nin[what] ? (const real_t*)arrays[k] : nullptr;
+    for (int k = 0; k < 5; ++k) a.x[k] = k < nin[what] ? (const real_t*)arrays[k] : nullptr;
     a.n = n > 0 ? n : 0;
     a.param = param;
     int parts = (int)((a.n + 1023) / 1024);

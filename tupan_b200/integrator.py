@@ -33,7 +33,7 @@ from .device import KERNEL_INPUTS, KERNEL_OUTPUTS, run as run_kernel
 from .sharded import ShardedKernel, shard_bounds
 
 CTL_T_CURR, CTL_TAU, CTL_T_END, CTL_ETA, CTL_NSTEPS, CTL_DONE, CTL_TAU_BASE, CTL_MIN_TS = range(8)
-RED_SUM, RED_KINETIC, RED_HALF_DOT, RED_SAKURA_DT, RED_ABS_MIN, RED_ABS_MAX = range(6)
+RED_SUM, RED_KINETIC, RED_HALF_DOT, RED_SAKURA_DT, RED_ABS_MIN, RED_ABS_MAX, RED_DOT, RED_MOMENT = range(8)
 
 R3, V3, A3, J3, S3, C3 = (("rx", "ry", "rz"), ("vx", "vy", "vz"), ("ax", "ay", "az"),
                           ("jx", "jy", "jz"), ("sx", "sy", "sz"), ("cx", "cy", "cz"))
@@ -212,7 +212,7 @@ class Integrator(object):
         self.ctl[CTL_T_CURR] = float(time)
         self.ctl[CTL_ETA] = self.eta
         self._t_end = None
-        self._scalar = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._scalar = torch.zeros(20, dtype=torch.float64, device=self.device)
         self._sharded = {}
         self.is_initialized = False
         # A Hermite / SIA step is a fixed sequence of launches whose only step-dependent input
@@ -372,6 +372,25 @@ class Integrator(object):
         self.reduce(RED_HALF_DOT, ("mass", "phi"), 3)
         ke, pe = self._scalar[2:4].cpu().tolist()
         return ke, pe
+
+    def diagnostics(self):
+        """The quantities of the reference's Diagnostic report (simulation.py:75-129): energies,
+        virial, centre of mass, linear and angular momentum -- reduced on the device, one
+        read-back of 17 doubles.  (Newtonian; the reference adds PN terms when enabled.)"""
+        self.force("phi_kernel", ("phi",))
+        self.reduce(RED_KINETIC, ("mass",) + V3, 0)
+        self.reduce(RED_HALF_DOT, ("mass", "phi"), 1)
+        self.reduce(RED_SUM, ("mass",), 2)
+        for c in range(3):
+            self.reduce(RED_DOT, ("mass", R3[c]), 3 + c)
+            self.reduce(RED_DOT, ("mass", V3[c]), 6 + c)
+            a, b = (c + 1) % 3, (c + 2) % 3
+            self.reduce(RED_MOMENT, ("mass", R3[a], R3[b], V3[a], V3[b]), 9 + c)
+        v = self._scalar[:12].cpu().tolist()
+        ke, pe, mtot = v[0], v[1], v[2]
+        return {"time": self.time, "ke": ke, "pe": pe, "te": ke + pe, "virial": 2 * ke + pe, "mtot": mtot,
+                "com_r": [x / mtot for x in v[3:6]], "com_v": [x / mtot for x in v[6:9]],
+                "lmom": v[6:9], "amom": v[9:12]}
 
     # ---- Hermite (integrator/hermite.py:390-410) ----------------------------------------------
     def _derivs(self, suffix):
