@@ -43,6 +43,13 @@ DP_INSTR_PER_PAIR = 32       # FP64-pipe instructions our kernel issues per pair
 S8 = ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz")
 OUT6 = ("ax", "ay", "az", "jx", "jy", "jz")
 METRIC = "acc_jerk pair-interactions/s fp64"
+# dram__bytes_read.sum + dram__bytes_write.sum of the pair kernel, per launch, from the one
+# `ncu --set full` capture of this command (profiles/r01_accjerk_v4_n1m_ncu_summary.txt):
+# 1.568 GB read + 1.358 GB written at N = 2^20 on one GPU.  It exceeds the 184.5 MB of
+# algorithmic bytes because the j range is split into 25 chunks for wave balance (each chunk
+# re-reads the i-state and writes a partial accumulator slot); at 1.3 GB/s it is 0.02 % of HBM
+# bandwidth -- this kernel is FP64-pipe bound.
+NCU_TRAFFIC = {(1 << 20, 1): 1567549000 + 1357939000}
 
 
 def parse():
@@ -313,7 +320,7 @@ def run_cuda(args):
     nominal_tf = sm_count * 64 * 2 * 1965e6 * 1e-12
     roofline = {
         "bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf, "traffic": None,
+        "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC.get((n, world)),
         "kernel": "pair_kernel<AccJerkOp<double>>", "kernel_ms": kern_ms,
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": local_pairs,
         "peak_source": "measured: pure-DFMA probe in this process (%.2f TFLOP/s = %d SMs x 64 lanes x 2 x %.0f MHz);"

@@ -42,7 +42,21 @@ int Context::fail(cudaError_t e, const char* where)
 
 int Context::init()
 {
-    if (ready) return 0;
+    if (ready) {
+        // One context (stream, staging buffers) per process, bound to the device that was current
+        // at the first call: one process per GPU, as torchrun launches them.  A caller that
+        // switches devices afterwards must hear about it instead of getting wrong-device pointers.
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != device) {
+            snprintf(last_msg, sizeof(last_msg),
+                     "tupan_cuda: the library context lives on device %d but device %d is current "
+                     "(one process per GPU)", device, cur);
+            fprintf(stderr, "%s\n", last_msg);
+            last_error = (int)cudaErrorInvalidDevice;
+            return last_error;
+        }
+        return 0;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return fail(e != cudaSuccess ? e : cudaErrorNoDevice, "no CUDA device");

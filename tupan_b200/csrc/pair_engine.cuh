@@ -357,22 +357,24 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
     a.prm = prm;
     if (ni <= 0) return cudaSuccess;
     const size_t smem = PairSmem<Op, U::TJ, U::STAGES>::BYTES;
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
     if (!plan.lane_split) {
         auto k = pair_kernel<Op, U::NT, Op::WPT, U::TJ, U::STAGES, false>;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static int attr_device = -1;             // function attributes are per device
+        if (attr_device != dev_id) {
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_done = true;
+            attr_device = dev_id;
         }
         const long long per_cta = (long long)U::NT * Op::WPT;
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
         k<<<grid, U::NT, smem, stream>>>(a);
     } else {
         auto k = pair_kernel<Op, U::NT_SPLIT, 1, U::TJ, U::STAGES, true>;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static int attr_device = -1;
+        if (attr_device != dev_id) {
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_done = true;
+            attr_device = dev_id;
         }
         const long long per_cta = (long long)(U::NT_SPLIT >> plan.js_log2);
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
