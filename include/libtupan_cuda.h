@@ -255,6 +255,15 @@ int tupan_cuda_axpy_dev(int narr, long long n, void *const *y, const void *const
 /* y[k] = x[k] / REAL(denom): r = mr / mtot, v = mv / mtot of nreg_x / nreg_v (nreg.py:28-30,51-53) */
 int tupan_cuda_scale_dev(int narr, long long n, void *const *y, const void *const *x, double denom,
                          void *stream);
+/* The post-Newtonian kick of the SIA integrators (kick_pn, integrator/sia.py:136-157) on either
+ * side of the pnacc evaluation, with the bookkeeping of PNbodyMethods (particles/body.py:471-527).
+ * arr = 23 device pointers: v[3] a[3] w[3] pna[3] mass r[3] pn_ke pn_mv[3] pn_am[3];
+ * step = REAL(c_inner * (c_outer * tau)).
+ *   phase 0:  v += (a step + w)/2
+ *   phase 1:  pn_ke -= (v . m pna) step; pn_mv -= m pna step; pn_am -= (r x m pna) step;
+ *             w = 2 pna step - w;  v += (a step + w)/2 */
+int tupan_cuda_pn_kick_dev(int phase, long long n, void *const *arr, double c_outer, double c_inner,
+                           const void *d_ctl, void *stream);
 /* t_curr += tau; tstep[:] = tau; time += tau; nstep += 1 (hermite.py:398-401; sia.py:1105-1113;
  * sakura.py:136-139).  Array pointers may be NULL. */
 int tupan_cuda_step_end_dev(long long n, void *d_time, void *d_nstep, void *d_tstep, void *d_ctl,

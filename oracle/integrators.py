@@ -44,6 +44,7 @@ class Bodies(object):
         self.a.setdefault("tstep", np.zeros(n, self.dtype))
         self.a.setdefault("nstep", np.zeros(n, utype))
         self.clock = [0.0]          # shared by every slice, like the class attribute t_curr
+        self.pn = None              # (order, clight) when post-Newtonian corrections are on
 
     @property
     def n(self):
@@ -103,6 +104,34 @@ class Bodies(object):
     def set_snap_crackle(self, jps):
         self._call("snap_crackle_kernel", S14, jps, (), ("sx", "sy", "sz", "cx", "cy", "cz"))
 
+    def set_pnacc(self, jps):                     # extensions.py:395-446, Clight :31-60
+        order, c = self.pn
+        inv = [(1.0 / c) ** k for k in range(1, 8)]
+        self._call("pnacc_kernel", S8, jps, [order] + inv, ("pnax", "pnay", "pnaz"))
+
+    # PNbodyMethods, particles/body.py:471-527
+    def pn_kick_ke(self, tau):
+        self.need("pn_ke")
+        pnfx, pnfy, pnfz = self.mass * self.pnax, self.mass * self.pnay, self.mass * self.pnaz
+        self.a["pn_ke"] -= (self.vx * pnfx + self.vy * pnfy + self.vz * pnfz) * tau
+
+    def pn_drift_com_r(self, tau):
+        self.need("pn_mrx", "pn_mry", "pn_mrz", "pn_mvx", "pn_mvy", "pn_mvz")
+        for c in "xyz":
+            self.a["pn_mr" + c] += self.a["pn_mv" + c] * tau
+
+    def pn_kick_lmom(self, tau):
+        self.need("pn_mvx", "pn_mvy", "pn_mvz")
+        for c in "xyz":
+            self.a["pn_mv" + c] -= (self.mass * self.a["pna" + c]) * tau
+
+    def pn_kick_amom(self, tau):
+        self.need("pn_amx", "pn_amy", "pn_amz")
+        pnfx, pnfy, pnfz = self.mass * self.pnax, self.mass * self.pnay, self.mass * self.pnaz
+        self.a["pn_amx"] -= (self.ry * pnfz - self.rz * pnfy) * tau
+        self.a["pn_amy"] -= (self.rz * pnfx - self.rx * pnfz) * tau
+        self.a["pn_amz"] -= (self.rx * pnfy - self.ry * pnfx) * tau
+
     def set_tstep(self, jps, eta):
         self._call("tstep_kernel", S8, jps, (eta,), ("tstep", "tstepij"))
 
@@ -121,8 +150,12 @@ class Bodies(object):
 
     # ---- diagnostics (particles/body.py:262-306, 364-368) -------------------------------
     @property
-    def kinetic_energy(self):
-        return float((0.5 * self.mass * (self.vx ** 2 + self.vy ** 2 + self.vz ** 2)).sum())
+    def kinetic_energy(self):                     # body.py:262-289 (+ pn_ke when PN is on)
+        ke = 0.5 * self.mass * (self.vx ** 2 + self.vy ** 2 + self.vz ** 2)
+        if self.pn:
+            self.need("pn_ke")
+            ke += self.a["pn_ke"]
+        return float(ke.sum())
 
     @property
     def potential_energy(self):
@@ -273,15 +306,30 @@ def palindrome(first, second):
     return seq + seq[-2::-1]
 
 
-def sia_drift(ips, tau):                         # drift_n, sia.py:64-71
+def sia_drift(ips, tau):                         # drift / drift_n / drift_pn, sia.py:64-71, 90-98, 165-173
     ips.a["rx"] += ips.vx * tau
     ips.a["ry"] += ips.vy * tau
     ips.a["rz"] += ips.vz * tau
+    if ips.pn:
+        ips.pn_drift_com_r(tau)
     return ips
 
 
-def sia_kick(ips, tau):                          # kick + kick_n, sia.py:77-84,179-186
+def sia_kick(ips, tau):                          # kick + kick_n / kick_pn, sia.py:77-84, 104-159, 179-186
     ips.set_acc(ips)
+    if ips.pn:                                   # the active branch of kick_pn, sia.py:136-157
+        ips.need("wx", "wy", "wz")
+        for c in "xyz":
+            ips.a["v" + c] += (ips.a["a" + c] * tau + ips.a["w" + c]) / 2
+        ips.set_pnacc(ips)
+        ips.pn_kick_ke(tau)
+        ips.pn_kick_lmom(tau)
+        ips.pn_kick_amom(tau)
+        for c in "xyz":
+            ips.a["w" + c][...] = 2 * ips.a["pna" + c] * tau - ips.a["w" + c]
+        for c in "xyz":
+            ips.a["v" + c] += (ips.a["a" + c] * tau + ips.a["w" + c]) / 2
+        return ips
     ips.a["vx"] += ips.ax * tau
     ips.a["vy"] += ips.ay * tau
     ips.a["vz"] += ips.az * tau
@@ -448,9 +496,11 @@ def sakura_do_step(ps, method, eta, tau):        # Sakura.do_step + get_sakura_t
 
 
 # ---- driver (simulation.py:187-201 + Base.evolve_step, integrator/__init__.py:80-99) ---------------
-def evolve(arrays, prec, method, eta, t_end, kind="oracle", t0=0.0, max_steps=None, threads=1):
-    """-> (Bodies after the run, number of steps)."""
+def evolve(arrays, prec, method, eta, t_end, kind="oracle", t0=0.0, max_steps=None, threads=1, pn=None):
+    """-> (Bodies after the run, number of steps).  pn = (order, clight) turns the post-Newtonian
+    corrections on (Base.__init__, integrator/__init__.py:24-37; SIA only, as in the reference)."""
     ps = Bodies(arrays, prec, kind, threads)
+    ps.pn = pn
     ps.clock[0] = t0
     sia = SIA(method, eta) if method.startswith("sia") else None
     nreg = None

@@ -8,6 +8,7 @@ Run in the build container only (needs /root/reference, gcc, cffi, scipy):
                                                                # sys.argv at import, ctype.py:13)
     python tests/golden/make_golden_integrators.py --config1   # adds BASELINE.json configs[0]:
                                                                # Plummer N=1024, (a)hermite4, t_end=1
+    python tests/golden/make_golden_integrators.py --pn_order  # post-Newtonian SIA runs (fp64)
 
 Each case stores the initial state, the state after the reference's own driver loop
 (`while abs(time) < t_end: evolve_step(t_end)`, simulation.py:187-201), the number of steps,
@@ -53,23 +54,36 @@ SMALL = [
     ("sakura", 32, 1.0 / 64, 0.125), ("asakura", 32, 1.0 / 16, 0.0625),
 ]
 CONFIG1 = [("hermite4", 1024, 1.0 / 64, 1.0), ("ahermite4", 1024, 1.0 / 64, 1.0)]
+# post-Newtonian SIA (kick_pn / drift_pn, sia.py:90-159): needs "--pn_order" in sys.argv at import
+# (particles/body.py:532); (method, n, eta, t_end, pn_order, clight).  kdk only: the dkd variants
+# touch pn_mvx before it is registered unless an earlier run in the same process created it.
+PN = [("sia21s.kdk", 32, 1.0 / 64, 0.0625, 7, 8.0), ("sia21a.kdk", 32, 1.0 / 16, 1.0 / 32, 7, 8.0),
+      ("sia43s.kdk", 32, 1.0 / 64, 0.0625, 7, 8.0), ("sia22a.kdk", 32, 1.0 / 16, 1.0 / 32, 4, 16.0),
+      ("sia21s.kdk", 32, 1.0 / 64, 0.0625, 2, 4.0)]
+PN_OUT = ("wx", "wy", "wz", "pn_ke", "pn_mrx", "pn_mry", "pn_mrz", "pn_mvx", "pn_mvy", "pn_mvz",
+          "pn_amx", "pn_amy", "pn_amz")
 
 
-def run_case(method, n, eta, t_end, seed=1):
+def run_case(method, n, eta, t_end, seed=1, pn_order=0, clight=None):
     ps = make_plummer(n, 4.0 / n, ("equalmass",), seed=seed)
     rec = {"in/" + k: np.array(getattr(ps, k)) for k in STATE}
+    type(ps).include_pn_corrections = False      # energies of the initial state are Newtonian
     ke0, pe0 = ps.kinetic_energy, ps.potential_energy
-    it = Integrator(eta, 0.0, ps, method=method)
+    if pn_order:
+        it = Integrator(eta, 0.0, ps, method=method, pn_order=pn_order, clight=clight)
+    else:
+        it = Integrator(eta, 0.0, ps, method=method)
     steps = 0
     t0 = time.time()
     while abs(it.time) < t_end:
         it.evolve_step(t_end)
         steps += 1
     ps = it.particle_system
-    for k in OUT + ("id",):
+    for k in OUT + ("id",) + (PN_OUT if pn_order else ()):
         rec["out/" + k] = np.array(getattr(ps, k))
-    ke1, pe1 = ps.kinetic_energy, ps.potential_energy
-    rec["meta"] = np.array([eta, t_end, steps, it.time, ke0, pe0, ke1, pe1], dtype=np.float64)
+    ke1, pe1 = ps.kinetic_energy, ps.potential_energy            # ke includes pn_ke when PN is on
+    rec["meta"] = np.array([eta, t_end, steps, it.time, ke0, pe0, ke1, pe1, pn_order, clight or 0.0],
+                           dtype=np.float64)
     print("%-4s %-12s n=%-5d steps=%-6d t=%.6f eerr=%+.3e  %.1fs" % (
         TAG, method, n, steps, it.time, ((ke1 + pe1) - (ke0 + pe0)) / (-pe1), time.time() - t0), flush=True)
     return rec
@@ -86,10 +100,14 @@ def main():
     if "--config1" in sys.argv:
         cases = list(CONFIG1)
         name = "integrators_config1"
+    if "--pn_order" in sys.argv:
+        cases = list(PN)
+        name = "integrators_pn"
     flat = {}
-    for method, n, eta, t_end in cases:
-        rec = run_case(method, n, eta, t_end)
-        key = "%s_n%d" % (method, n)
+    for case in cases:
+        method, n, eta, t_end = case[:4]
+        rec = run_case(method, n, eta, t_end, 1, *case[4:])
+        key = "%s_n%d" % (method, n) + ("_pn%d_c%g" % case[4:] if len(case) > 4 else "")
         for k, v in rec.items():
             flat[key + "/" + k] = v
     path = os.path.join(HERE, "%s_%s.npz" % (name, TAG))

@@ -23,7 +23,9 @@ def test_method_names_are_the_reference_ones():
     with pytest.raises(ValueError):
         Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="rk4", device="cpu")
     with pytest.raises(NotImplementedError):
-        Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="sia21s.dkd", device="cpu", pn_order=7, clight=128)
+        Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="hermite4", device="cpu", pn_order=7, clight=128)
+    with pytest.raises(TypeError):          # integrator/__init__.py:27-32
+        Integrator(1.0 / 64, 0.0, ics.make_plummer(8), method="sia21s.kdk", device="cpu", pn_order=7)
 
 
 def test_no_cpu_fallback():

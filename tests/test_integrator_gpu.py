@@ -140,3 +140,42 @@ def test_device_diagnostics_match_numpy():
     assert np.allclose(d["amom"], (m * np.cross(r.T, v.T).T).sum(1), rtol=1e-12, atol=1e-15)
     ke, pe = it.energies()
     assert d["pe"] == pe and d["virial"] == pytest.approx(2 * ke + pe, rel=1e-14)
+
+
+PN_ARRAYS = ("wx", "wy", "wz", "pn_ke", "pn_mrx", "pn_mry", "pn_mrz", "pn_mvx", "pn_mvy", "pn_mvz",
+             "pn_amx", "pn_amy", "pn_amz")
+
+
+def test_post_newtonian_sia_against_reference_golden_runs():
+    """kick_pn / drift_pn with the PN bookkeeping (sia.py:90-159, body.py:471-527), orders 2, 4, 7,
+    strong fields (clight = 4...16) so that the PN terms matter."""
+    cases = load_integrator_cases("float64", "integrators_pn")
+    for name, (ins, outs, meta) in sorted(cases.items()):
+        method = name.split("_n", 1)[0]
+        eta, t_end, steps_ref, t_ref = meta[:4]
+        ps = system_from(ins, "float64")
+        it = Integrator(eta, 0.0, ps, method=method, pn_order=int(meta[8]), clight=float(meta[9]))
+        steps = it.evolve(t_end, check_every=4)
+        ke1, pe1 = it.energies()
+        out = it.particle_system
+        assert steps == int(steps_ref) and it.time == t_ref, name
+        for k in VEC:
+            assert rel(getattr(out, k), outs[k]) <= 1e-10, (name, k)
+        for k in PN_ARRAYS:
+            scale = max(np.max(np.abs(outs[k])), 1e-300)
+            assert np.max(np.abs(getattr(out, k) - outs[k])) <= 1e-9 * scale + 1e-18, (name, k)
+        assert ke1 == pytest.approx(meta[6], rel=1e-11) and pe1 == pytest.approx(meta[7], rel=1e-11), name
+
+
+def test_post_newtonian_dkd_against_oracle():
+    src = ics.make_plummer(200, seed=4)
+    ins = {k: getattr(src, k).copy() for k in ("mass", "eps2") + VEC}
+    ref, steps_ref = oi.evolve(ins, "float64", "sia22s.dkd", 1.0 / 64, 1.0 / 16, pn=(7, 16.0))
+    ps = system_from(ins, "float64")
+    it = Integrator(1.0 / 64, 0.0, ps, method="sia22s.dkd", pn_order=7, clight=16.0)
+    steps = it.evolve(1.0 / 16, check_every=4)
+    out = it.particle_system
+    assert steps == steps_ref
+    for k in VEC + ("pn_mrx", "pn_ke", "pn_amz", "wx"):
+        scale = np.max(np.abs(ref.a[k]))
+        assert np.max(np.abs(getattr(out, k) - ref.a[k])) <= 1e-9 * scale + 1e-18, k

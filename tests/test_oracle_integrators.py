@@ -54,3 +54,20 @@ def test_operator_sequences():
         seq = oi.palindrome(B, A)
         assert abs(sum(c for w, c in seq if w == 0) - 1) < 1e-14, name
         assert abs(sum(c for w, c in seq if w == 1) - 1) < 1e-14, name
+
+
+def test_oracle_post_newtonian_sia_reproduces_reference_bit_for_bit():
+    """kick_pn / drift_pn and the PN bookkeeping arrays (sia.py:90-159, body.py:471-527)."""
+    cases = load_integrator_cases("float64", "integrators_pn")
+    assert len(cases) >= 5
+    for name, (ins, outs, meta) in sorted(cases.items()):
+        method = name.split("_n", 1)[0]
+        eta, t_end, steps, t_final = meta[:4]
+        pn = (int(meta[8]), float(meta[9]))
+        ps, nsteps = oi.evolve(ins, "float64", method, eta, t_end, pn=pn)
+        assert nsteps == int(steps) and float(ps.clock[0]) == t_final, name
+        for k in outs:
+            if k == "id":
+                continue
+            assert np.array_equal(ps.a[k], outs[k]), (name, k)
+        assert ps.kinetic_energy == meta[6] and ps.potential_energy == meta[7], name

@@ -89,6 +89,8 @@ PART2 = {
                                             ctypes.c_double, ctypes.c_void_p]),
     "tupan_cuda_step_end_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_pn_kick_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double,
+                                              ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
     "tupan_cuda_stamp_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_double, ctypes.c_void_p]),
     "tupan_cuda_reduce_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double,

@@ -196,6 +196,58 @@ __global__ void __launch_bounds__(256) scale_kernel(const VecRefs a, double deno
 }
 
 // ---------------------------------------------------------------------------------------
+// Post-Newtonian kick of the SIA integrators (kick_pn, sia.py:136-157) around the pnacc
+// evaluation, with the bookkeeping of PNbodyMethods (particles/body.py:471-527):
+//   phase 0:  v += (a tau + w)/2
+//   phase 1:  pn_ke -= (v . m pna) tau;  pn_mv -= m pna tau;  pn_am -= (r x m pna) tau;
+//             w = 2 pna tau - w;  v += (a tau + w)/2
+// ---------------------------------------------------------------------------------------
+struct PnRefs {
+    real_t* v[3];
+    const real_t* a[3];
+    real_t* w[3];
+    const real_t* pna[3];
+    const real_t* mass;
+    const real_t* r[3];
+    real_t* pn_ke;
+    real_t* pn_mv[3];
+    real_t* pn_am[3];
+    long long n;
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(256) pn_kick_kernel(const PnRefs p, double c_outer, double c_inner,
+                                                      const double* __restrict__ ctl)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const double tau_d = ctl ? ctl[CTL_TAU] : 1.0;
+    const real_t tau = (real_t)(c_inner * (c_outer * tau_d));
+    real_t v[3], a[3], w[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { v[c] = p.v[c][i]; a[c] = p.a[c][i]; w[c] = p.w[c][i]; }
+    if (PHASE == 1) {
+        const real_t m = p.mass[i];
+        real_t f[3], r[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { f[c] = m * p.pna[c][i]; r[c] = p.r[c][i]; }
+        p.pn_ke[i] = p.pn_ke[i] - ((v[0] * f[0] + v[1] * f[1]) + v[2] * f[2]) * tau;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p.pn_mv[c][i] = p.pn_mv[c][i] - f[c] * tau;
+        p.pn_am[0][i] = p.pn_am[0][i] - (r[1] * f[2] - r[2] * f[1]) * tau;
+        p.pn_am[1][i] = p.pn_am[1][i] - (r[2] * f[0] - r[0] * f[2]) * tau;
+        p.pn_am[2][i] = p.pn_am[2][i] - (r[0] * f[1] - r[1] * f[0]) * tau;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            w[c] = (real_t)2 * p.pna[c][i] * tau - w[c];
+            p.w[c][i] = w[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.v[c][i] = v[c] + (a[c] * tau + w[c]) / (real_t)2;
+}
+
+// ---------------------------------------------------------------------------------------
 // step_end: t_curr += tau; tstep[:] = tau; time += tau; nstep += 1
 // (hermite.py:398-401, sia.py:1105-1113, sakura.py:136-139)
 // ---------------------------------------------------------------------------------------
@@ -457,6 +509,38 @@ int tupan_cuda_step_end_dev(long long n, void* d_time, void* d_nstep, void* d_ts
     step_end_kernel<<<blocks_for(m), 256, 0, (cudaStream_t)stream>>>(n, (real_t*)d_time, (abi_uint*)d_nstep,
                                                                      (real_t*)d_tstep, (double*)d_ctl);
     TUPAN_CHECK(cudaGetLastError(), "step_end_kernel");
+    c->launches++;
+    return 0;
+}
+
+int tupan_cuda_pn_kick_dev(int phase, long long n, void* const* arr, double c_outer, double c_inner,
+                           const void* d_ctl, void* stream)
+{
+    Context* c;
+    std::lock_guard<std::mutex> lock(ctx().mu);
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if (phase != 0 && phase != 1) return c->fail(cudaErrorInvalidValue, "pn_kick phase");
+    if (n <= 0) return 0;
+    PnRefs p;
+    for (int k = 0; k < 3; ++k) {
+        p.v[k] = (real_t*)arr[k];
+        p.a[k] = (const real_t*)arr[3 + k];
+        p.w[k] = (real_t*)arr[6 + k];
+        p.pna[k] = (const real_t*)arr[9 + k];
+        p.r[k] = (const real_t*)arr[13 + k];
+        p.pn_mv[k] = (real_t*)arr[17 + k];
+        p.pn_am[k] = (real_t*)arr[20 + k];
+    }
+    p.mass = (const real_t*)arr[12];
+    p.pn_ke = (real_t*)arr[16];
+    p.n = n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (phase == 0)
+        pn_kick_kernel<0><<<blocks_for(n), 256, 0, s>>>(p, c_outer, c_inner, (const double*)d_ctl);
+    else
+        pn_kick_kernel<1><<<blocks_for(n), 256, 0, s>>>(p, c_outer, c_inner, (const double*)d_ctl);
+    TUPAN_CHECK(cudaGetLastError(), "pn_kick_kernel");
     c->launches++;
     return 0;
 }

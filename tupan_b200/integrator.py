@@ -160,6 +160,10 @@ class _Lib(object):
                                                         self.ptrs(d1), ctl.data_ptr(), self.stream()),
                 "hermite_correct")
 
+    def pn_kick(self, phase, n, arrays, c_outer, c_inner, ctl):
+        self.ok(self.lib.tupan_cuda_pn_kick_dev(phase, n, self.ptrs(arrays), c_outer, c_inner, ctl.data_ptr(),
+                                                self.stream()), "pn_kick")
+
     def axpy(self, n, y, x, c_outer=1.0, c_inner=1.0, ctl=None):
         self.ok(self.lib.tupan_cuda_axpy_dev(len(y), n, self.ptrs(y), self.ptrs(x), c_outer, c_inner,
                                              ctl.data_ptr() if ctl is not None else None, self.stream()), "axpy")
@@ -186,8 +190,17 @@ class Integrator(object):
         if method not in self.PROVIDED_METHODS:
             raise ValueError("Unexpected integration method: %r. Provided methods: %s"
                              % (method, self.PROVIDED_METHODS))
-        if pn_order:
-            raise NotImplementedError("post-Newtonian kicks are not device-resident yet")
+        # Base.__init__, integrator/__init__.py:24-37
+        self.pn = None
+        if pn_order and pn_order > 0:
+            if clight is None:
+                raise TypeError("'clight' is not defined. Please set the speed of light argument 'clight' "
+                                "when using 'pn_order' > 0.")
+            if not (method and method.startswith("sia") and method[5] in "sa"):
+                raise NotImplementedError("post-Newtonian corrections: shared-step SIA methods only "
+                                          "(the reference's Hermite/NREG/Sakura have none either)")
+            inv1 = 1.0 / float(clight)
+            self.pn = (int(pn_order),) + tuple(inv1 ** k for k in range(1, 8))     # extensions.py:31-60
         self.reporter = kwargs.pop("reporter", None)
         for k in ("viewer", "dumpper", "dump_freq", "gl_freq"):
             kwargs.pop(k, None)
@@ -370,6 +383,11 @@ class Integrator(object):
         self.force("phi_kernel", ("phi",))
         self.reduce(RED_KINETIC, ("mass",) + V3, 2)
         self.reduce(RED_HALF_DOT, ("mass", "phi"), 3)
+        if self.pn:                                        # ke += pn_ke, body.py:283-287
+            self.st.need("pn_ke")
+            self.reduce(RED_SUM, ("pn_ke",), 4)
+            ke, pe, pn_ke = self._scalar[2:5].cpu().tolist()
+            return ke + pn_ke, pe
         ke, pe = self._scalar[2:4].cpu().tolist()
         return ke, pe
 
@@ -446,10 +464,22 @@ class Integrator(object):
         else:
             self._begin()
         r, v, a = st.need(*R3), st.need(*V3), st.need(*A3)
+        if self.pn:
+            PNA, PMR, PMV = ("pnax", "pnay", "pnaz"), ("pn_mrx", "pn_mry", "pn_mrz"), ("pn_mvx", "pn_mvy", "pn_mvz")
+            pn_arr = st.need(*(V3 + A3 + ("wx", "wy", "wz") + PNA + ("mass",) + R3 + ("pn_ke",) + PMV
+                               + ("pn_amx", "pn_amy", "pn_amz")))
+            pmr, pmv = st.need(*PMR), st.need(*PMV)
         for wb in self._bridge:
             for is_drift, w in self._evolve:
                 if is_drift:
                     L.axpy(st.n, r, v, wb, w, self.ctl)    # drift_n
+                    if self.pn:                            # drift_pn: pn_drift_com_r
+                        L.axpy(st.n, pmr, pmv, wb, w, self.ctl)
+                elif self.pn:                              # kick = set_acc + kick_pn (sia.py:136-157)
+                    self.force("acc_kernel", A3)
+                    L.pn_kick(0, st.n, pn_arr, wb, w, self.ctl)
+                    self.force("pnacc_kernel", PNA, self.pn)
+                    L.pn_kick(1, st.n, pn_arr, wb, w, self.ctl)
                 else:
                     self.force("acc_kernel", A3)           # kick = set_acc + kick_n
                     L.axpy(st.n, v, a, wb, w, self.ctl)
