@@ -38,7 +38,8 @@ def _compile(args):
     obj = os.path.join(LIBDIR, "obj", "%s_%s.o" % (unit, tag))
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
         return unit, tag, "cached", ""
-    cmd = ([NVCC] + FLAGS + UNIT_FLAGS.get(unit, []) + (["-DTUPAN_FP64"] if tag == "fp64" else [])
+    cmd = ([NVCC] + FLAGS + UNIT_FLAGS.get(unit, []) + os.environ.get("TUPAN_NVCC_EXTRA", "").split()
+           + (["-DTUPAN_FP64"] if tag == "fp64" else [])
            + ["-c", src, "-o", obj])
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:

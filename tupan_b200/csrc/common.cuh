@@ -145,6 +145,23 @@ TUPAN_DEV InvR<T> soft_inv(T x, T r2)
     return o;
 }
 
+// 1/x without the IEEE-division slow path (a call inside a hot loop): MUFU.RCP64H seed (20
+// bits) and one third-order step, y (1 + e + e^2) with e = 1 - x y; error ~ e^3 < 2^-58.
+TUPAN_DEV double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+TUPAN_DEV float rcp_fast(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 TUPAN_DEV double rmax(double a, double b) { return fmax(a, b); }
 TUPAN_DEV float rmax(float a, float b) { return fmaxf(a, b); }
 TUPAN_DEV double rsqrt_full(double a) { return 1.0 / sqrt(a); }

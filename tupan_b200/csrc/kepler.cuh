@@ -231,35 +231,53 @@ template <typename T> TUPAN_DEV void twobody_leapfrog(T dt, T m, T e2, State<T>&
     p.x = fma(p.vx, half, p.x); p.y = fma(p.vy, half, p.y); p.z = fma(p.vz, half, p.z);
 }
 
-// Wide or fast pairs take the leapfrog, the rest the Kepler map (:94-123).
-template <typename T> TUPAN_DEV void twobody_step(T dt, T m, T e2, State<T>& p)
+// Wide or fast pairs take the leapfrog, the rest the Kepler map (:94-123):
+//     R = 64 (m / v2);  r2 > R^2 ? leapfrog : universal_kepler_solver
+// FAST = true is the in-line half of the deferring sweep (pair_engine.cuh).  It takes the
+// leapfrog only when the choice is beyond doubt -- r2 v2^2 > 4096 m^2 (1 + 2^-36) (fp32: 2^-18), a
+// test without the division, whose margin covers any rounding of either form --, leaves a masked
+// pair (r2 > 0 false) unchanged as kepler_propagate would, and returns false for everything else; the caller parks such a pair and re-runs it from its initial state with
+// FAST = false, i.e. with the reference's own test.  Parking is always safe.
+template <bool FAST, typename T> TUPAN_DEV bool twobody_step(T dt, T m, T e2, State<T>& p)
 {
     const T r2 = p.x * p.x + p.y * p.y + p.z * p.z;
     const T v2 = p.vx * p.vx + p.vy * p.vy + p.vz * p.vz;
+    if (FAST) {
+        const T margin = sizeof(T) == 8 ? T(1.4551915228366852e-11) : T(3.814697265625e-6);  // 2^-36, 2^-18
+        const T lhs = r2 * (v2 * v2);
+        const T rhs = (m * m) * (T(4096) * (T(1) + margin));
+        if (lhs > rhs) {
+            twobody_leapfrog(dt, m, e2, p);
+            return true;
+        }
+        return !(r2 > T(0));   // masked pair: unchanged, as kepler_propagate would return it
+    }
     const T R = T(64) * (m / v2);
     if (r2 > R * R) twobody_leapfrog(dt, m, e2, p);
     else p = kepler_propagate(dt, m, e2, p);
+    return true;
 }
 
 // flag in {-2,-1,1,2}: where the free drift is taken out (:126-191); other values: no-op.
-template <typename T> TUPAN_DEV void twobody_evolve(T dt, int flag, T m, T e2, State<T>& p)
+template <bool FAST, typename T> TUPAN_DEV bool twobody_evolve(T dt, int flag, T m, T e2, State<T>& p)
 {
     if (flag == -1) {
         p.x -= p.vx * dt; p.y -= p.vy * dt; p.z -= p.vz * dt;
-        twobody_step(dt, m, e2, p);
+        return twobody_step<FAST>(dt, m, e2, p);
     } else if (flag == 1) {
-        twobody_step(dt, m, e2, p);
+        if (!twobody_step<FAST>(dt, m, e2, p)) return false;
         p.x -= p.vx * dt; p.y -= p.vy * dt; p.z -= p.vz * dt;
     } else if (flag == -2) {
         const T h = dt / T(2);
         p.x -= p.vx * h; p.y -= p.vy * h; p.z -= p.vz * h;
-        twobody_step(dt, m, e2, p);
+        if (!twobody_step<FAST>(dt, m, e2, p)) return false;
         p.x -= p.vx * h; p.y -= p.vy * h; p.z -= p.vz * h;
     } else if (flag == 2) {
-        twobody_step(dt / T(2), m, e2, p);
+        if (!twobody_step<FAST>(dt / T(2), m, e2, p)) return false;
         p.x -= p.vx * dt; p.y -= p.vy * dt; p.z -= p.vz * dt;
-        twobody_step(dt / T(2), m, e2, p);
+        return twobody_step<FAST>(dt / T(2), m, e2, p);
     }
+    return true;
 }
 
 // =======================================================================================
@@ -280,7 +298,10 @@ template <typename T> struct SakuraOp {
     }
     static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row8(j, r, row); }
     static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
-    static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p)
+    // Deferring sweep (pair_engine.cuh): leapfrog pairs are finished in line, pairs that need
+    // the Kepler solver are described by D_* and solved later with full warps.
+    enum { D_X, D_Y, D_Z, D_VX, D_VY, D_VZ, D_M, D_E2, D_MJ, ND };
+    static TUPAN_DEV bool pair_fast(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p, T (&d)[ND])
     {
         State<T> p0;
         p0.x = s[IX] - row[JX]; p0.y = s[IY] - row[JY]; p0.z = s[IZ] - row[JZ];
@@ -288,10 +309,24 @@ template <typename T> struct SakuraOp {
         const T e2 = s[IE] + row[J8_E2];
         const T m = s[IM] + row[JM];
         State<T> q = p0;
-        twobody_evolve(p.dt, p.flag, m, e2, q);
-        const T mu = row[JM] / m;
-        a[0] = fma(mu, q.x - p0.x, a[0]); a[1] = fma(mu, q.y - p0.y, a[1]); a[2] = fma(mu, q.z - p0.z, a[2]);
-        a[3] = fma(mu, q.vx - p0.vx, a[3]); a[4] = fma(mu, q.vy - p0.vy, a[4]); a[5] = fma(mu, q.vz - p0.vz, a[5]);
+        if (twobody_evolve<true>(p.dt, p.flag, m, e2, q)) {
+            const T mu = row[JM] * rcp_fast(m);
+            a[0] = fma(mu, q.x - p0.x, a[0]); a[1] = fma(mu, q.y - p0.y, a[1]); a[2] = fma(mu, q.z - p0.z, a[2]);
+            a[3] = fma(mu, q.vx - p0.vx, a[3]); a[4] = fma(mu, q.vy - p0.vy, a[4]); a[5] = fma(mu, q.vz - p0.vz, a[5]);
+            return false;
+        }
+        d[D_X] = p0.x; d[D_Y] = p0.y; d[D_Z] = p0.z; d[D_VX] = p0.vx; d[D_VY] = p0.vy; d[D_VZ] = p0.vz;
+        d[D_M] = m; d[D_E2] = e2; d[D_MJ] = row[JM];
+        return true;
+    }
+    static TUPAN_DEV void pair_slow(const T (&d)[ND], const Params& p, T (&c)[NA])
+    {
+        const State<T> p0 = {d[D_X], d[D_Y], d[D_Z], d[D_VX], d[D_VY], d[D_VZ]};
+        State<T> q = p0;
+        twobody_evolve<false>(p.dt, p.flag, d[D_M], d[D_E2], q);
+        const T mu = d[D_MJ] / d[D_M];
+        c[0] = mu * (q.x - p0.x); c[1] = mu * (q.y - p0.y); c[2] = mu * (q.z - p0.z);
+        c[3] = mu * (q.vx - p0.vx); c[4] = mu * (q.vy - p0.vy); c[5] = mu * (q.vz - p0.vz);
     }
     static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
     static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
@@ -300,6 +335,8 @@ template <typename T> struct SakuraOp {
         for (int k = 0; k < NO; ++k) out[k][i] = a[k];
     }
 };
+
+template <typename T> struct Defers<SakuraOp<T>> { enum { value = 1 }; };
 
 // =======================================================================================
 // Two-body Kepler kernel -- replaces kepler_solver_kernel (kepler_solver_kernel.c:5-50).

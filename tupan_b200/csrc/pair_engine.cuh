@@ -26,6 +26,18 @@
 //   pack_j(const real* const* jarr, long long j, real (&row)[NJP])
 //   zero(real (&a)[NA]);  pair(s, row, a, prm);  combine(a, b)
 //   finish(iarr, i, a, prm, real* const* out)
+//
+// Ops whose pairs are cheap most of the time and very expensive now and then (sakura: a
+// leapfrog for wide pairs, a universal-variable Kepler solve for close ones) set
+// Defers<Op>::value and supply, instead of pair():
+//   enum { ND };                                    reals that describe one deferred pair
+//   bool pair_fast(s, row, a, prm, real (&d)[ND])   cheap case: accumulate, return false;
+//                                                   expensive case: fill d, return true
+//   pair_slow(d, prm, real (&c)[NA])                full evaluation of one deferred pair
+// pair_kernel_defer parks the expensive pairs of a warp in a shared-memory ring and runs them
+// 32 at a time, one per lane, so the slow path executes with full warps instead of dragging 31
+// idle lanes along each time one lane hits it.  Results return to the owner lane in ring order,
+// which for any given particle is its own j order: the sums stay deterministic.
 #pragma once
 #include "common.cuh"
 
@@ -84,6 +96,20 @@ template <class Op, int TJ, int STAGES> struct PairSmem {
     enum {
         TILE_BYTES = TJ * Packed<Op>::ROW_BYTES,
         BYTES = STAGES * TILE_BYTES + STAGES * 8
+    };
+};
+
+template <class Op> struct Defers { enum { value = 0 }; };
+
+template <class Op, int NT, int TJ, int STAGES, bool DEFER = (Defers<Op>::value != 0)> struct PairSmemDefer {
+    enum { QCAP = 64, QUEUE_OFF = 0, WARP_BYTES = 0, BYTES = PairSmem<Op, TJ, STAGES>::BYTES };
+};
+template <class Op, int NT, int TJ, int STAGES> struct PairSmemDefer<Op, NT, TJ, STAGES, true> {
+    enum {
+        QCAP = 64,   // ring slots per warp: < 32 waiting + at most 32 pushed by one j step
+        QUEUE_OFF = (PairSmem<Op, TJ, STAGES>::BYTES + 15) / 16 * 16,
+        WARP_BYTES = QCAP * (Op::ND * (int)sizeof(typename Op::real) + (int)sizeof(int)),
+        BYTES = QUEUE_OFF + (NT / 32) * WARP_BYTES
     };
 };
 
@@ -222,6 +248,222 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
 }
 
 // ---------------------------------------------------------------------------------------
+// pair_kernel_defer: the same sweep for Ops with a rare expensive case (see the top of the
+// file).  One i-particle per thread.  The j loop is warp-uniform (lane split: a predicate
+// instead of a per-lane trip count) because pushing into the warp's ring is a warp collective.
+//
+// The kernel is glue around two functions that are deliberately NOT inlined:
+//   sweep_rows     the hot loop over the rows of a tile; call-free, so its registers are
+//                  allocated on their own terms.  (Inlined next to the solver call, ptxas homed
+//                  every loop-carried value -- i-state, accumulators -- in local memory for
+//                  the whole loop: 29 Gpair/s in fp64.)  It returns when the tile is finished or
+//                  the ring holds a full warp of deferred pairs;
+//   the solver     (Op::pair_slow's own __noinline__ function, e.g. kepler_propagate).
+// The state that crosses those calls lives in a small struct in local memory, read once per
+// call (a tile of 128 rows) and written back once.
+// ---------------------------------------------------------------------------------------
+template <class Op> struct SweepState {
+    typename Op::real is[Op::NI];
+    typename Op::real acc[Op::NA];
+    int qhead, qcount;   // the warp's ring of deferred pairs: first slot, pairs waiting
+};
+
+// Rows [k, steps) of one tile (lane split: row k*js + jsub) until the ring is full.  Returns
+// the next k.
+template <class Op, bool LANE_SPLIT>
+__device__ __noinline__ int sweep_rows(SweepState<Op>* st, const typename Op::real* sj, int cnt, int k, int steps,
+                                       int jsl, int jsub, int lane, typename Op::real* qdat, int* qown,
+                                       typename Op::Params prm)
+{
+    typedef typename Op::real T;
+    constexpr int NJP = Packed<Op>::NJP, ND = Op::ND, NA = Op::NA, QCAP = 64;
+    T is[Op::NI], acc[NA];
+#pragma unroll
+    for (int q = 0; q < Op::NI; ++q) is[q] = st->is[q];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) acc[q] = st->acc[q];
+    const int qhead = st->qhead;
+    int qcount = st->qcount;
+    for (; k < steps && qcount < 32; ++k) {
+        const int j = LANE_SPLIT ? (k << jsl) + jsub : k;
+        bool need = false;
+        T d[ND];
+        if (!LANE_SPLIT || j < cnt) {
+            T row[NJP];
+            load_row<Op>(sj + j * NJP, row);
+            need = Op::pair_fast(is, row, acc, prm, d);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m != 0u) {
+            if (need) {
+                const int slot = (qhead + qcount + __popc(m & ((1u << lane) - 1u))) & (QCAP - 1);
+#pragma unroll
+                for (int q = 0; q < ND; ++q) qdat[slot * ND + q] = d[q];
+                qown[slot] = lane;
+            }
+            qcount += __popc(m);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) st->acc[q] = acc[q];
+    st->qcount = qcount;
+    return k;
+}
+
+// One deferred pair: description in slot[0..ND), result out in slot[0..NA).  Inlined into the
+// glue kernel on purpose: as a __noinline__ function that itself calls the __noinline__ solver,
+// nvcc 12.9 produced wrong results for softened pairs (bisected on a B200 against the golden
+// vectors); the hot loop is unaffected either way, it lives in sweep_rows.
+template <class Op>
+__device__ __forceinline__ void deferred_pair(typename Op::real* slot, typename Op::Params prm)
+{
+    typedef typename Op::real T;
+    T d[Op::ND], c[Op::NA];
+#pragma unroll
+    for (int k = 0; k < Op::ND; ++k) d[k] = slot[k];
+    Op::pair_slow(d, prm, c);
+#pragma unroll
+    for (int k = 0; k < Op::NA; ++k) slot[k] = c[k];
+}
+
+template <class Op, int NT, int TJ, int STAGES, bool LANE_SPLIT>
+__global__ void __launch_bounds__(NT) pair_kernel_defer(const __grid_constant__ PairArgs<Op> a)
+{
+    typedef typename Op::real T;
+    typedef PairSmemDefer<Op, NT, TJ, STAGES, true> SM;
+    constexpr int NJP = Packed<Op>::NJP;
+    constexpr int TILE_ELEMS = TJ * NJP;
+    constexpr int ND = Op::ND, NA = Op::NA, QCAP = SM::QCAP;
+    static_assert(NA <= ND, "results are handed back through the ring slots");
+    static_assert(QCAP == 64, "sweep_rows assumes a 64-slot ring");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tiles = reinterpret_cast<T*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * TILE_ELEMS * sizeof(T));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    T* qdat = reinterpret_cast<T*>(smem_raw + SM::QUEUE_OFF + (tid >> 5) * SM::WARP_BYTES);  // [QCAP][ND]
+    int* qown = reinterpret_cast<int*>(qdat + QCAP * ND);                                     // [QCAP]
+
+    const int jsl = LANE_SPLIT ? a.js_log2 : 0;
+    const int js = 1 << jsl;
+    const int jsub = tid & (js - 1);
+    const int islot = tid >> jsl;
+    const int slots = NT >> jsl;
+    const long long ibase = (long long)blockIdx.x * slots;
+
+    SweepState<Op> st;
+    {
+        long long i = ibase + islot;
+        if (i > a.ni - 1) i = a.ni - 1;  // clamp: computes a duplicate, never stored
+        Op::load_i(a.i.p, i, st.is);
+        Op::zero(st.acc);
+        st.qhead = 0;
+        st.qcount = 0;
+    }
+
+    const long long jlo = a.j0 + (long long)blockIdx.y * a.jchunk;
+    long long jhi = jlo + a.jchunk;
+    if (jhi > a.j1) jhi = a.j1;
+    const int ntiles = (jhi > jlo) ? (int)((jhi - jlo + TJ - 1) / TJ) : 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int s = t % STAGES;
+        const long long r0 = jlo + (long long)t * TJ;
+        long long cnt = jhi - r0;
+        if (cnt > TJ) cnt = TJ;
+        const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(tiles + s * TILE_ELEMS, a.jpack + r0 * NJP, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < STAGES && t < ntiles; ++t) issue(t);
+    }
+
+    // run the n (<= 32) oldest deferred pairs of this warp, one per lane, and hand the results
+    // to their owner lanes in ring order (for any one particle: its own j order)
+    auto drain = [&](int n) {
+        __syncwarp();
+        const int qhead = st.qhead;
+        if (lane < n) deferred_pair<Op>(qdat + ((qhead + lane) & (QCAP - 1)) * ND, a.prm);
+        __syncwarp();
+        for (int e = 0; e < n; ++e) {
+            const int slot = (qhead + e) & (QCAP - 1);
+            if (qown[slot] == lane) {
+                T c[NA];
+#pragma unroll
+                for (int k = 0; k < NA; ++k) c[k] = qdat[slot * ND + k];
+                Op::combine(st.acc, c);
+            }
+        }
+        __syncwarp();
+        st.qhead = (qhead + n) & (QCAP - 1);
+        st.qcount -= n;
+    };
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
+        const T* sj = tiles + s * TILE_ELEMS;
+        long long rem = jhi - (jlo + (long long)t * TJ);
+        const int cnt = rem > TJ ? TJ : (int)rem;
+        const int steps = (cnt + js - 1) >> jsl;
+        int k = 0;
+        while (true) {
+            k = sweep_rows<Op, LANE_SPLIT>(&st, sj, cnt, k, steps, jsl, jsub, lane, qdat, qown, a.prm);
+            if (st.qcount >= 32) drain(32);
+            else break;                      // ring not full: the tile is finished
+        }
+        __syncthreads();  // every warp is done with stage s -> it may be refilled
+        if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+    }
+    while (st.qcount > 0) drain(st.qcount < 32 ? st.qcount : 32);
+
+    T acc[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[k] = st.acc[k];
+    if (LANE_SPLIT) {
+        for (int off = js >> 1; off > 0; off >>= 1) {
+            T other[NA];
+#pragma unroll
+            for (int k = 0; k < NA; ++k) other[k] = __shfl_xor_sync(0xffffffffu, acc[k], off);
+            Op::combine(acc, other);
+        }
+    }
+
+    if (jsub == 0) {
+        const long long i = ibase + islot;
+        if (i < a.ni) {
+            if (a.partial != nullptr) {
+                T* dst = a.partial + ((long long)(a.slot0 + blockIdx.y) * NA) * a.ni + i;
+#pragma unroll
+                for (int k = 0; k < NA; ++k) dst[(long long)k * a.ni] = acc[k];
+            } else {
+                Op::finish(a.i.p, i, acc, a.prm, a.out.p);
+            }
+        }
+    }
+}
+
+// The kernel an Op runs on: <throughput shape> and <lane split>.
+template <class Op, bool LANE_SPLIT> struct KernelOf {
+    typedef void (*Fn)(const PairArgs<Op>);
+    template <int NT, int TJ, int STAGES> static Fn get()
+    {
+        if constexpr (Defers<Op>::value != 0) return pair_kernel_defer<Op, NT, TJ, STAGES, LANE_SPLIT>;
+        else return pair_kernel<Op, NT, LANE_SPLIT ? 1 : Op::WPT, TJ, STAGES, LANE_SPLIT>;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // finalize_kernel: combine nslots raw accumulator sets and apply the epilogue.
 // ---------------------------------------------------------------------------------------
 template <class Op>
@@ -268,8 +510,8 @@ inline int throughput_slots(const DeviceInfo& dev)
     typedef Tune<Op> U;
     static int occ = 0;
     if (occ == 0) {
-        auto k = pair_kernel<Op, U::NT, Op::WPT, U::TJ, U::STAGES, false>;
-        const size_t smem = PairSmem<Op, U::TJ, U::STAGES>::BYTES;
+        auto k = KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES>();
+        const size_t smem = PairSmemDefer<Op, U::NT, U::TJ, U::STAGES>::BYTES;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, U::NT, smem) != cudaSuccess || n < 1) {
@@ -356,11 +598,11 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
     a.out = out;
     a.prm = prm;
     if (ni <= 0) return cudaSuccess;
-    const size_t smem = PairSmem<Op, U::TJ, U::STAGES>::BYTES;
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     if (!plan.lane_split) {
-        auto k = pair_kernel<Op, U::NT, Op::WPT, U::TJ, U::STAGES, false>;
+        auto k = KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES>();
+        const size_t smem = PairSmemDefer<Op, U::NT, U::TJ, U::STAGES>::BYTES;
         static int attr_device = -1;             // function attributes are per device
         if (attr_device != dev_id) {
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -370,7 +612,8 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
         k<<<grid, U::NT, smem, stream>>>(a);
     } else {
-        auto k = pair_kernel<Op, U::NT_SPLIT, 1, U::TJ, U::STAGES, true>;
+        auto k = KernelOf<Op, true>::template get<U::NT_SPLIT, U::TJ, U::STAGES>();
+        const size_t smem = PairSmemDefer<Op, U::NT_SPLIT, U::TJ, U::STAGES>::BYTES;
         static int attr_device = -1;
         if (attr_device != dev_id) {
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
