@@ -25,6 +25,27 @@ void DevBuf::release()
     cap = 0;
 }
 
+void* HostBuf::ensure(size_t bytes)
+{
+    if (bytes <= cap && p) return p;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+        p = nullptr;
+        return nullptr;
+    }
+    cap = want;
+    return p;
+}
+void HostBuf::release()
+{
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
 Context& ctx()
 {
     static Context c;

@@ -8,6 +8,8 @@ static inline TstepParams<real_t> tstep_params(const double* s)
 {
     TstepParams<real_t> p;
     p.eta = (real_t)s[0];
+    p.eta_k1 = p.eta * (real_t)0.5;
+    p.eta_k2 = p.eta * (real_t)0.375;
     return p;
 }
 TUPAN_DEFINE_VTABLE(vt_phi, PhiOp<real_t>, "phi_kernel", 5, 1, 0, 14, no_params)

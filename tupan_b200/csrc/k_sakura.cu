@@ -72,9 +72,30 @@ int kepler_run_host(long long pairs, const real_t* const* hin, double dt, real_t
     int rc = c.init();
     if (rc) return rc;
     if (pairs <= 0) return 0;
-    const size_t bytes = (size_t)(2 * pairs) * sizeof(real_t);
+    const size_t n = (size_t)(2 * pairs), bytes = n * sizeof(real_t);
     const real_t* din[8];
     real_t* dout[6];
+    // the reference calls this with ONE binary (16 + 12 values): one pinned block, one copy each way
+    const size_t stride = (n + 3) / 4 * 4;
+    if (14 * stride * sizeof(real_t) <= (size_t)(1 << 20)) {
+        real_t* hs = static_cast<real_t*>(c.stage_host.ensure(14 * stride * sizeof(real_t)));
+        real_t* ds = static_cast<real_t*>(c.stage_dev.ensure(14 * stride * sizeof(real_t)));
+        if (!hs || !ds) return c.fail(cudaErrorMemoryAllocation, "kepler staging block");
+        for (int k = 0; k < 8; ++k) {
+            memcpy(hs + k * stride, hin[k], bytes);
+            din[k] = ds + k * stride;
+        }
+        for (int k = 0; k < 6; ++k) dout[k] = ds + (8 + k) * stride;
+        TUPAN_CHECK(cudaMemcpyAsync(ds, hs, 8 * stride * sizeof(real_t), cudaMemcpyHostToDevice, c.stream),
+                    "H2D kepler block");
+        rc = kepler_run_dev(pairs, din, dt, dout, c.stream);
+        if (rc) return rc;
+        TUPAN_CHECK(cudaMemcpyAsync(hs + 8 * stride, ds + 8 * stride, 6 * stride * sizeof(real_t),
+                                    cudaMemcpyDeviceToHost, c.stream), "D2H kepler block");
+        TUPAN_CHECK(cudaStreamSynchronize(c.stream), "synchronize");
+        for (int k = 0; k < 6; ++k) memcpy(hout[k], hs + (8 + k) * stride, bytes);
+        return kepler_limit_check("kepler_solver_kernel");
+    }
     for (int k = 0; k < 8; ++k) {
         real_t* d = static_cast<real_t*>(c.in_i[k].ensure(bytes));
         if (!d) return c.fail(cudaErrorMemoryAllocation, "kepler in");

@@ -239,7 +239,12 @@ template <typename T> struct SnapCrackleOp {
 // eta/sqrt(1+.) is tstep_kernel.c:46-47.  The lane/chunk reduction of the second
 // accumulator is a max, as is the fused minimum time-step (see finish_min in api).
 // =======================================================================================
-template <typename T> struct TstepParams { T eta; };
+// FP64-pipe instructions per pair: 6 (differences) + 1 (2m) + 3 (r2) + 2 (e2, x) + 3 (r.v) + 3 (v2)
+// + 6 (1/r, 1/r2) + 1 (2 phi) + 2 (w2) + 2 (gamma) + 5 (eta/sqrt w2) + 1 + 1 (w2 -= ..) + 2 (sum, max)
+// = 39.  Two factors ride for free: the masses are stored doubled (i-state and packed row; an
+// exact scaling, so 2 phi = (2m) / r bit for bit), and eta is folded into the constants of the
+// second rsqrt step.
+template <typename T> struct TstepParams { T eta, eta_k1, eta_k2; };   // eta, eta/2, 3 eta/8
 template <typename T> struct TstepOp {
     typedef T real;
     typedef TstepParams<T> Params;
@@ -248,28 +253,32 @@ template <typename T> struct TstepOp {
     enum { IX, IY, IZ, IE, IVX, IVY, IVZ, IM };
     static TUPAN_DEV void load_i(const T* const* a, long long i, T (&s)[NI])
     {
-        s[IM] = a[0][i];
+        s[IM] = T(2) * a[0][i];
         s[IX] = a[1][i]; s[IY] = a[2][i]; s[IZ] = a[3][i]; s[IE] = a[4][i];
         s[IVX] = a[5][i]; s[IVY] = a[6][i]; s[IVZ] = a[7][i];
     }
-    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP]) { pack_row8(j, r, row); }
+    static TUPAN_DEV void pack_j(const T* const* j, long long r, T (&row)[NJP])
+    {
+        pack_row8(j, r, row);
+        row[JM] = T(2) * row[JM];
+    }
     static TUPAN_DEV void zero(T (&a)[NA]) { zero_all(a); }
     static TUPAN_DEV void pair(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p)
     {
         T rx = s[IX] - row[JX], ry = s[IY] - row[JY], rz = s[IZ] - row[JZ];
         T vx = s[IVX] - row[J8_VX], vy = s[IVY] - row[J8_VY], vz = s[IVZ] - row[J8_VZ];
-        T m = s[IM] + row[JM];
+        T m2 = s[IM] + row[JM];                                   // 2 (mi + mj)
         T r2 = rx * rx; r2 = fma(ry, ry, r2); r2 = fma(rz, rz, r2);
         T x = r2 + (s[IE] + row[J8_E2]);
         T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
         T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
         InvR<T> w = soft_inv<true>(x, r2);
         // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv
-        T phi = m * w.r1;
-        T w2 = w.r2 * fma(T(2), phi, v2);
-        T gamma = w.r2 * fma(T(2) * w.r2, phi, w2);
+        T phi2 = m2 * w.r1;
+        T w2 = w.r2 * (v2 + phi2);
+        T gamma = w.r2 * fma(w.r2, phi2, w2);
         // masked pair: w2 is exactly 0, its own exponent masks the seed -> gamma 0 -> w2 stays 0
-        gamma *= p.eta * rsqrt_scaled<true>(w2, w2, T(1), T(0.5), T(0.375));
+        gamma *= rsqrt_scaled<true>(w2, w2, p.eta, p.eta_k1, p.eta_k2);
         w2 = fma(-gamma, rv, w2);
         a[0] += w2;
         a[1] = rmax(w2, a[1]);
