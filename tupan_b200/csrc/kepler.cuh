@@ -337,6 +337,7 @@ template <typename T> struct SakuraOp {
 };
 
 template <typename T> struct Defers<SakuraOp<T>> { enum { value = 1 }; };
+template <typename T> struct OpCost<SakuraOp<T>> { enum { value = 62 }; };
 
 // =======================================================================================
 // Two-body Kepler kernel -- replaces kepler_solver_kernel (kepler_solver_kernel.c:5-50).

@@ -378,4 +378,13 @@ template <typename T> struct NregVOp {
     }
 };
 
+// FP-pipe instructions per pair (launch-plan model, pair_engine.cuh)
+template <typename T> struct OpCost<PhiOp<T>> { enum { value = 14 }; };
+template <typename T> struct OpCost<AccOp<T>> { enum { value = 19 }; };
+template <typename T> struct OpCost<AccJerkOp<T>> { enum { value = 32 }; };
+template <typename T> struct OpCost<SnapCrackleOp<T>> { enum { value = 75 }; };
+template <typename T> struct OpCost<TstepOp<T>> { enum { value = 39 }; };
+template <typename T> struct OpCost<NregXOp<T>> { enum { value = 30 }; };
+template <typename T> struct OpCost<NregVOp<T>> { enum { value = 16 }; };
+
 }  // namespace tupan

@@ -523,52 +523,79 @@ inline int throughput_slots(const DeviceInfo& dev)
     return occ * dev.sm_count;
 }
 
-// Launch shape.
-//   * throughput shape (WPT particles per thread, unrolled j loop) whenever the i-blocks times
-//     the j chunks available can fill every CTA slot of the chip.  All CTAs of a wave run for as
-//     long as the longest of them, so the chunk length (in tiles) is chosen to minimise
-//     waves x (tiles per chunk + a fixed per-CTA cost): N = 2^20 on 8 GPUs has 256 i-blocks for
-//     296 slots -- one chunk would idle 14 % of the chip, 37 chunks of 28 tiles make 32 full waves;
-//   * lane split (several lanes per particle) for small ni.
+// Issue cost of one pair on the kernel's main pipe, in warp instructions (FP64 or FP32); the
+// launch-plan model below only needs it to within ~20 %.  Specialised next to each Op.
+template <class Op> struct OpCost { enum { value = 32 }; };
+
+// Launch shape: the candidate with the smallest predicted time.
+//
+// The model was fitted to forced-plan sweeps on a B200 (tools/plan_probe.py,
+// profiles/r01_plan_probe_accjerk.txt).  What it encodes:
+//   * throughput shape (WPT particles per thread, unrolled j loop, j range cut into g chunks
+//     over blockIdx.y).  A CTA's 8 warps keep an SM's pipe busy on their own, and CTAs are
+//     handed out greedily, so the SM -- not the CTA slot -- is the unit of load balance:
+//     a launch lasts as long as the busiest SM, which gets ceil(CTAs / SMs) chunks (measured to
+//     within 2 % at N = 4096 ... 16384).  N = 4096 (8 i-blocks): 16 chunks of 2 tiles on 128 SMs
+//     take 57 us where the old wave-count rule chose a 32-lane split at 190 us;
+//   * lane split (2^js lanes of a warp share one particle, 128-thread CTAs).  One warp per
+//     SM sub-partition per CTA: bounded by the dependent-instruction latency of the rows a
+//     lane owns, by the pipe when several CTAs share an SM, and by a per-tile hand-shake;
+//   * g > 1 costs a finalize launch that reads g accumulator sets.
 template <class Op>
 inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
 {
     typedef Tune<Op> U;
-    Plan p = {0, 0, 1};
+    typedef typename Op::real T;
+    Plan best_plan = {0, 0, 1};
     const int TJ = U::TJ;
-    const long long IB = (long long)U::NT * Op::WPT;
-    const long long iblocks = (ni + IB - 1) / IB;
-    const long long slots = throughput_slots<Op>(dev);
-    const long long tiles = (nj + TJ - 1) / TJ;
-    const long long min_tiles = 2;                 // a chunk is at least 2 tiles (256 rows)
-    long long maxg = tiles / min_tiles;
-    if (maxg > 64) maxg = 64;
-    if (maxg < 1) maxg = 1;
-    if (iblocks * maxg >= slots && ni * 10 >= iblocks * IB * 9) {
-        double best = 1e300;
+    const double sms = dev.sm_count > 0 ? dev.sm_count : 148;
+    const double clk_per_us = 1965.0;
+    const bool dp = sizeof(T) == 8;
+    const double cpw = OpCost<Op>::value * (dp ? 2.33 : 1.3);   // pipe clocks per warp per row
+    const double lat = OpCost<Op>::value * (dp ? 6.25 : 5.0);   // clocks per row for a lone warp
+    const long long tiles = nj > 0 ? (nj + TJ - 1) / TJ : 1;
+    const double fin_bytes_per_us = 2.0e6;
+    auto finalize_us = [&](long long g) {
+        return g > 1 ? 9.0 + (double)g * (double)ni * Op::NA * sizeof(T) / fin_bytes_per_us : 0.0;
+    };
+    double best = 1e300;
+
+    {   // throughput shape
+        const long long IB = (long long)U::NT * Op::WPT;
+        const long long iblocks = (ni + IB - 1) / IB;
+        const double tile_us = (double)TJ * Op::WPT * cpw * (U::NT / 32 / 4) / clk_per_us;
+        const long long maxg = tiles < 64 ? tiles : 64;
         for (long long g = 1; g <= maxg; ++g) {
             const long long tpc = (tiles + g - 1) / g;            // tiles per chunk
             const long long chunks = (tiles + tpc - 1) / tpc;     // non-empty chunks
             if (chunks != g) continue;                            // same split as a smaller g
-            const long long ctas = iblocks * chunks;
-            const long long waves = (ctas + slots - 1) / slots;
-            const double cost = (double)waves * ((double)tpc + 0.5) + 0.02 * (double)g;
-            if (cost < best) { best = cost; p.jg = (int)g; }
+            const double ctas = (double)iblocks * chunks;
+            const double per_sm = (double)((long long)((ctas + sms - 1) / sms));
+            // equal CTAs handed out greedily: the busiest SM runs ceil(CTAs / SMs) of them
+            const double busiest = per_sm * (tpc + 0.1);       // + prologue/epilogue of each CTA
+            const double t = 8.0 + busiest * tile_us + finalize_us(chunks);
+            if (t < best) { best = t; best_plan.lane_split = 0; best_plan.js_log2 = 0; best_plan.jg = (int)g; }
         }
-        return p;
     }
-    const long long resident = (long long)dev.sm_count * 512;  // threads we want in flight
-    p.lane_split = 1;
-    // lanes per particle: enough to fill the chip, never more than a tile can feed
-    while (p.js_log2 < 5 && (ni << p.js_log2) < resident && (TJ >> (p.js_log2 + 1)) >= 4) p.js_log2++;
-    long long threads = ni << p.js_log2;
-    long long want = (resident + threads - 1) / threads;        // j chunks to fill the rest
-    long long mg = (nj + 4 * TJ - 1) / (4 * TJ);                // >= 4 tiles per chunk
-    if (want > mg) want = mg;
-    if (want > 64) want = 64;
-    if (want < 1) want = 1;
-    p.jg = (int)want;
-    return p;
+    for (int js = 0; js <= 5 && (TJ >> js) >= 4; ++js) {          // lane split
+        const long long per_cta = U::NT_SPLIT >> js;
+        const long long icta = (ni + per_cta - 1) / per_cta;
+        for (long long g = 1; g <= 64 && g <= tiles; g *= 2) {
+            const long long tpc = (tiles + g - 1) / g;
+            const double rows_per_lane = (double)tpc * TJ / (1 << js);
+            const double ctas = (double)icta * g;
+            const double per_sm = (double)((long long)((ctas + sms - 1) / sms));
+            const double pipe = per_sm * rows_per_lane * cpw * 1.15;
+            const double chain = rows_per_lane * lat;
+            // every CTA walks the same tiles at the same time: the more of them (and the fewer rows a
+            // lane takes from each), the longer the hand-over of a tile
+            const double per_tile = 0.3 + ctas / 1000.0 + 0.15 * js;
+            const double t = 13.0 + 0.3 * js + (per_sm - 1.0) + (pipe > chain ? pipe : chain) / clk_per_us
+                             + per_tile * tpc + finalize_us(g);
+            if (t < best) { best = t; best_plan.lane_split = 1; best_plan.js_log2 = js; best_plan.jg = (int)g; }
+        }
+    }
+    return best_plan;
 }
 
 // Sweep rows [j0, j1) of `jpack` for all ni particles.

@@ -219,4 +219,7 @@ template <typename T, int LEVEL> struct PNAccOp {
     }
 };
 
+// FP-pipe instructions per pair (launch-plan model): ~45 for the Newtonian frame + ~60 per level
+template <typename T, int LEVEL> struct OpCost<PNAccOp<T, LEVEL>> { enum { value = 45 + 60 * LEVEL }; };
+
 }  // namespace tupan
