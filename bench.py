@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--n", type=int, default=1 << 20, help="particles (BASELINE: 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--transport", default=None, choices=("nccl", "p2p"),
+                    help="multi-GPU j rows: NCCL all-gather (default) or read in place through peer mappings")
     return ap.parse_args()
 
 
@@ -234,7 +236,7 @@ def run_cuda(args):
     out = {a: torch.empty(ni, dtype=torch.float64, device=dev) for a in OUT6}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     if world > 1:
-        sk = sharded.ShardedKernel("acc_jerk_kernel", n, torch.float64, dev)
+        sk = sharded.ShardedKernel("acc_jerk_kernel", n, torch.float64, dev, transport=args.transport)
 
         def step():
             flush.zero_()
@@ -355,7 +357,9 @@ def run_cuda(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "Plummer sphere N=%d equal-mass, eps=4/N, acc_jerk fp64 (one Hermite force "
-                               "evaluation)" % n, "n": n, "parallelism": "i-shard x%d, j all-gather" % world,
+                               "evaluation)" % n, "n": n, "parallelism": "i-shard x%d, %s" % (
+                                   world, "j rows read in place over NVLink (peer mappings)"
+                                   if world > 1 and sk.transport == "p2p" else "j all-gather"),
                    "l2": "256 MiB buffer written between steps (inside the timed region)",
                    "plan": {"lane_split": plan[0].value, "js_log2": plan[1].value, "jg": plan[2].value}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

@@ -187,6 +187,26 @@ int tupan_cuda_sweep_dev(int kernel, long long ni, const void *const *iarr, cons
 int tupan_cuda_finalize_dev(int kernel, long long ni, const void *const *iarr, const void *partial,
                             int nslots, const double *scal, void *const *out, void *stream);
 
+/* ---- Part 2b: packed rows in peer-visible memory (one process per GPU, NVLink/NVSwitch) ----
+ * The multi-GPU path needs every rank's packed rows on every GPU.  With these calls the rows are
+ * not copied at all: each rank packs into a buffer its peers have mapped (CUDA IPC), the ranks
+ * meet at a device-side barrier on their streams, and tupan_cuda_sweep_dev is pointed at the
+ * peer's buffer -- the pair kernel's TMA bulk copies then pull the tiles over NVLink while the
+ * previous tiles are being computed.  New work; the reference has no multi-device path. */
+/* allocate `bytes` of zeroed device memory other processes can map; handle64: 64 bytes out */
+int tupan_cuda_peer_alloc(long long bytes, void **dptr, void *handle64);
+/* map a buffer another process of this node allocated with tupan_cuda_peer_alloc */
+int tupan_cuda_peer_open(const void *handle64, void **dptr);
+int tupan_cuda_peer_close(void *dptr);
+int tupan_cuda_peer_free(void *dptr);
+/* barrier between the `world` ranks on `stream` (asynchronous for the host).  flags[r] is rank
+ * r's flag block (>= (world + 1) * 4 bytes from tupan_cuda_peer_alloc, mapped by everybody);
+ * the epoch counter lives in that block, so the call can be captured in a CUDA graph.  A peer
+ * that does not arrive within timeout_s is reported by tupan_cuda_peer_timeouts(). */
+int tupan_cuda_peer_barrier_dev(void *const *flags, int rank, int world, double timeout_s, void *stream);
+/* barriers that gave up since the last call (synchronises the device) */
+long long tupan_cuda_peer_timeouts(void);
+
 /* min over i of |tstep[i]| on the device (the host-side reduction of
  * tupan/particles/body.py:364-368 fused behind tstep); result is written to *d_min. */
 int tupan_cuda_abs_min_dev(long long n, const void *d_values, void *d_min, void *stream);

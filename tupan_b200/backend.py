@@ -62,6 +62,13 @@ PART2 = {
                                                ctypes.c_void_p]),
     "tupan_cuda_abs_min_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p]),
+    "tupan_cuda_peer_alloc": (ctypes.c_int, [ctypes.c_longlong, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "tupan_cuda_peer_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "tupan_cuda_peer_close": (ctypes.c_int, [ctypes.c_void_p]),
+    "tupan_cuda_peer_free": (ctypes.c_int, [ctypes.c_void_p]),
+    "tupan_cuda_peer_barrier_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                   ctypes.c_void_p]),
+    "tupan_cuda_peer_timeouts": (ctypes.c_longlong, []),
     "tupan_cuda_init": (ctypes.c_int, []),
     "tupan_cuda_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "tupan_cuda_clear_error": (None, []),

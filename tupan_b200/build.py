@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-UNITS = ["abi", "context", "k_newton", "k_snap", "k_nreg", "k_pn", "k_sakura", "k_update"]
+UNITS = ["abi", "context", "peer", "k_newton", "k_snap", "k_nreg", "k_pn", "k_sakura", "k_update"]
 # k_update evaluates the O(N) integrator updates in the reference's numpy operation order, one
 # rounding per operation: no FMA contraction in that unit.
 UNIT_FLAGS = {"k_update": ["-fmad=false"]}

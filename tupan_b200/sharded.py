@@ -9,6 +9,12 @@ sweeps the local rows; the remote rows are swept when they have landed, and one 
 combines the raw accumulator slots and applies the kernel's epilogue.  (The reference has no
 multi-device path at all; this is new work)
 
+``transport="p2p"`` removes the copy altogether: every rank packs into a buffer its peers have
+mapped through CUDA IPC (:class:`PeerRows`), the ranks meet at a device-side barrier, and each
+sweep is pointed at the owner's buffer -- the pair kernel's TMA bulk copies pull the tiles over
+NVLink/NVSwitch while the previous tiles are being computed (Part 2b of
+include/libtupan_cuda.h).  No gathered buffer, no NCCL on the data path.
+
 The collective and the arithmetic are reached through two small seams so the partition /
 gather / slot bookkeeping can be tested on CPU with the gloo backend:
 
@@ -56,9 +62,14 @@ class CudaEngine(object):
     def n_acc(self, kernel, scal):
         return self.lib.tupan_cuda_n_acc(backend.KERNEL_IDS[kernel], scal_array(scal))
 
+    @staticmethod
+    def _addr(buf):
+        """A tensor or a raw device address (rows that live in a peer's memory)."""
+        return ctypes.c_void_p(buf if isinstance(buf, int) else buf.data_ptr())
+
     def pack(self, kernel, jt, scal, packed):
         self._ok(self.lib.tupan_cuda_pack_dev(backend.KERNEL_IDS[kernel], jt[0].numel(), self._ptrs(jt),
-                                              scal_array(scal), ctypes.c_void_p(packed.data_ptr()),
+                                              scal_array(scal), self._addr(packed),
                                               self._stream()), "pack")
 
     def sweep_slots(self, kernel, ni, rows, scal):
@@ -66,7 +77,7 @@ class CudaEngine(object):
 
     def sweep(self, kernel, it, packed, j0, j1, scal, partial, slot0):
         self._ok(self.lib.tupan_cuda_sweep_dev(backend.KERNEL_IDS[kernel], it[0].numel(), self._ptrs(it),
-                                               ctypes.c_void_p(packed.data_ptr()), j0, j1, scal_array(scal),
+                                               self._addr(packed), j0, j1, scal_array(scal),
                                                ctypes.c_void_p(partial.data_ptr()), slot0, self._stream()),
                  "sweep")
 
@@ -77,6 +88,76 @@ class CudaEngine(object):
                  "finalize")
 
 
+class PeerRows(object):
+    """This rank's packed-row buffer and flag block, mapped by every rank of the group, and the
+    peers' buffers mapped here (CUDA IPC; one process per GPU on one node)."""
+
+    FLAG_BYTES = 256
+    TIMEOUT_S = 20.0
+
+    def __init__(self, lib, nbytes, group=None):
+        self.lib = lib
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._own = []
+        self._mapped = []
+
+        def alloc(n):
+            p, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            rc = lib.tupan_cuda_peer_alloc(int(n), ctypes.byref(p), h)
+            if rc != 0:
+                backend.check(lib, "peer_alloc")
+                raise backend.TupanCudaError("peer_alloc failed with code %d" % rc)
+            self._own.append(p.value)
+            return p.value, h.raw
+
+        rows, hrows = alloc(nbytes)
+        flags, hflags = alloc(self.FLAG_BYTES)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (hrows, hflags), group=group)
+        self.rows = [None] * self.world
+        self.flags = [None] * self.world
+        for r, (hr, hf) in enumerate(handles):
+            if r == self.rank:
+                self.rows[r], self.flags[r] = rows, flags
+                continue
+            for h, dst in ((hr, self.rows), (hf, self.flags)):
+                p = ctypes.c_void_p()
+                rc = lib.tupan_cuda_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p))
+                if rc != 0:
+                    backend.check(lib, "peer_open")
+                    raise backend.TupanCudaError("peer_open failed with code %d" % rc)
+                dst[r] = p.value
+                self._mapped.append(p.value)
+        self._flag_array = (ctypes.c_void_p * self.world)(*self.flags)
+        dist.barrier(group=group)        # nobody signals a flag block that is not mapped everywhere yet
+
+    def barrier(self):
+        """All ranks meet on their current streams; asynchronous for the host."""
+        rc = self.lib.tupan_cuda_peer_barrier_dev(self._flag_array, self.rank, self.world, self.TIMEOUT_S,
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            backend.check(self.lib, "peer_barrier")
+            raise backend.TupanCudaError("peer_barrier failed with code %d" % rc)
+
+    def check(self):
+        """Synchronise and fail loudly if a barrier gave up waiting for a peer."""
+        hits = self.lib.tupan_cuda_peer_timeouts()
+        if hits != 0:
+            raise backend.TupanCudaError("peer barrier: %d wait(s) timed out (or CUDA error)" % hits)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)   # no peer may still be reading
+        for p in self._mapped:
+            self.lib.tupan_cuda_peer_close(ctypes.c_void_p(p))
+        dist.barrier(group=self.group)
+        for p in self._own:
+            self.lib.tupan_cuda_peer_free(ctypes.c_void_p(p))
+        self._mapped, self._own = [], []
+
+
 class ShardedKernel(object):
     """One pairwise kernel, i-sharded over the ranks of ``group``.
 
@@ -85,9 +166,10 @@ class ShardedKernel(object):
     """
 
     OVERLAP_MIN_PAIRS = 2.0e9      # ~4 ms of acc_jerk fp64 on a B200
+    MAX_ROW_WIDTH = 16             # reals per packed row, widest kernel (snap_crackle: 14, padded)
 
     def __init__(self, kernel, n_total, dtype=torch.float64, device="cuda", group=None, engine=None,
-                 overlap=True):
+                 overlap=True, transport=None):
         self.kernel = kernel
         self.n = int(n_total)
         self.group = group
@@ -105,6 +187,15 @@ class ShardedKernel(object):
         self._packed = None
         self._partial = None
         self._width = None
+        # "nccl": all-gather of the packed rows; "p2p": rows stay where they were packed and are
+        # read through peer mappings (GPUs of one node only)
+        import os
+        self.transport = transport or os.environ.get("TUPAN_B200_TRANSPORT", "nccl")
+        if self.transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+        if self.world == 1 or not self.on_cuda:
+            self.transport = "nccl"
+        self.peer = None
 
     # rows of rank r live at [r * rows_max, r * rows_max + count_r) of the gathered buffer
     def segments(self, split_local=True):
@@ -131,7 +222,58 @@ class ShardedKernel(object):
             self._packed = torch.zeros(self.world * self.rows_max * width, dtype=self.dtype, device=self.device)
         return self._packed, width
 
+    _peer_cache = {}
+
+    def _peer_rows(self):
+        """One mapped buffer per (group, element size, rows) shared by every kernel of the process."""
+        if self.peer is None:
+            esize = torch.empty(0, dtype=self.dtype).element_size()
+            key = (id(self.group), esize, self.rows_max)
+            if key not in ShardedKernel._peer_cache:
+                nbytes = self.rows_max * self.MAX_ROW_WIDTH * esize
+                ShardedKernel._peer_cache[key] = PeerRows(self.engine.lib, nbytes, self.group)
+            self.peer = ShardedKernel._peer_cache[key]
+        return self.peer
+
+    def evaluate_p2p(self, local, scalars=(), out=None):
+        """The same evaluation with the rows left in their owners' memory."""
+        ins = KERNEL_INPUTS[self.kernel]
+        it = [local[a] for a in ins]
+        ni = self.hi - self.lo
+        if it[0].numel() != ni:
+            raise ValueError("rank %d owns %d particles, got %d" % (self.rank, ni, it[0].numel()))
+        if out is None:
+            out = {a: torch.empty(ni, dtype=self.dtype, device=self.device) for a in KERNEL_OUTPUTS[self.kernel]}
+        ot = [out[a] for a in KERNEL_OUTPUTS[self.kernel]]
+        eng = self.engine
+        peer = self._peer_rows()
+        if eng.row_width(self.kernel, scalars) > self.MAX_ROW_WIDTH:
+            raise ValueError("packed row wider than the peer buffer")
+        if ni > 0:
+            eng.pack(self.kernel, it, scalars, peer.rows[self.rank])
+        peer.barrier()                               # every rank's rows are in place
+        # own rows first, then the peers round-robin so that no two ranks pull from the same GPU
+        order = [(self.rank + k) % self.world for k in range(self.world)]
+        segs = [(r, self.bounds[r + 1] - self.bounds[r]) for r in order]
+        segs = [(r, cnt) for (r, cnt) in segs if cnt > 0]
+        nslots = [eng.sweep_slots(self.kernel, ni, cnt, scalars) for (_, cnt) in segs]
+        na = eng.n_acc(self.kernel, scalars)
+        need = sum(nslots) * na * max(ni, 1)
+        if self._partial is None or self._partial.numel() < need:
+            self._partial = torch.empty(need, dtype=self.dtype, device=self.device)
+        slot = 0
+        for (r, cnt), ns in zip(segs, nslots):
+            if ni > 0:
+                eng.sweep(self.kernel, it, peer.rows[r], 0, cnt, scalars, self._partial, slot)
+            slot += ns
+        peer.barrier()                               # everybody is done reading: rows may be repacked
+        if ni > 0:
+            eng.finalize(self.kernel, it, self._partial, slot, scalars, ot)
+        return out
+
     def evaluate(self, local, scalars=(), out=None):
+        if self.transport == "p2p":
+            return self.evaluate_p2p(local, scalars, out)
         ins = KERNEL_INPUTS[self.kernel]
         it = [local[a] for a in ins]
         ni = self.hi - self.lo
