@@ -58,7 +58,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=("cuda", "reference"))
-    ap.add_argument("--n", type=int, default=1 << 20, help="particles (BASELINE: 2^20)")
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1 << 20,
+                    help="particles (BASELINE: 2^20); spell it --particles under torchrun, whose own parser\n"
+                         "takes --n for an abbreviation of its options")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--transport", default=None, choices=("nccl", "p2p"),

@@ -43,12 +43,12 @@ def main():
     # key=value tokens on purpose: torchrun's own parser abbreviation-matches long options that
     # follow the script name (--n -> --nnodes ...)
     opts = {"n": 1024, "method": "ahermite4", "eta": 1.0 / 64, "t_end": 1.0, "prec": "float64", "seed": 1,
-            "max_steps": None, "check_every": 16, "graph": None}
+            "max_steps": None, "check_every": 16, "graph": None, "plan": None}
     for tok in sys.argv[1:]:
         k, v = tok.split("=", 1)
         if k not in opts:
             raise SystemExit("unknown option %r (known: %s)" % (k, ", ".join(sorted(opts))))
-        opts[k] = v if k in ("method", "prec") else (int(v) if k in ("n", "seed", "max_steps", "check_every", "graph")
+        opts[k] = v if k in ("method", "prec", "plan") else (int(v) if k in ("n", "seed", "max_steps", "check_every", "graph")
                                                      else float(v))
     args = argparse.Namespace(**opts)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -59,6 +59,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = backend.require_gpu(args.prec)
+    if args.plan:                                # plan=split,js,jg forces the launch shape of every pair kernel
+        lib.tupan_cuda_force_plan(*[int(x) for x in args.plan.split(",")])
     ps = ics.make_plummer(args.n, seed=args.seed, dtype=args.prec)
     it = Integrator(args.eta, 0.0, ps, method=args.method, device=dev,
                     graph=None if args.graph is None else bool(args.graph))
@@ -77,7 +79,8 @@ def main():
     if rank == 0:
         per = evals_per_step(args.method)
         print(json.dumps({
-            "config": "Plummer N=%d %s eta=%g t_end=%g %s" % (args.n, args.method, args.eta, args.t_end, args.prec),
+            "config": "Plummer N=%d %s eta=%g t_end=%g %s%s" % (args.n, args.method, args.eta, args.t_end, args.prec,
+                                                              " plan=" + args.plan if args.plan else ""),
             "n_gpus": world, "steps": steps, "t": it.time, "ke0": ke0, "pe0": pe0, "ke1": ke1, "pe1": pe1,
             "eerr": ((ke1 + pe1) - (ke0 + pe0)) / (-pe1), "wall_s": wall, "timed_steps": timed,
             "steps_per_s": timed / wall, "us_per_step": 1e6 * wall / max(timed, 1),

@@ -142,8 +142,14 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
     const int tid = threadIdx.x;
     const int jsl = LANE_SPLIT ? a.js_log2 : 0;
     const int js = 1 << jsl;
-    const int jsub = tid & (js - 1);
-    const int islot = tid >> jsl;
+    // Lane split: the lanes of a warp are laid out particle-minor -- lane = jsub * ipw + (particle
+    // within the warp), ipw = 32 / js -- so that neighbouring lanes read the SAME packed row (a
+    // shared-memory broadcast).  Row-minor (lane = particle * js + jsub) made the 8 lanes of a
+    // quarter warp read 8 rows 64 bytes apart: a 4-way bank conflict on every LDS.128, which is
+    // what bounded the split kernels (N = 4096, 8 lanes per particle: 150 us).
+    const int ipw = 32 >> jsl;                        // particles per warp
+    const int jsub = (tid & 31) >> (5 - jsl);
+    const int islot = (tid >> 5) * ipw + (tid & (ipw - 1));
     const int slots = NT >> jsl;
     const long long ibase = (long long)blockIdx.x * (slots * WPT);
 
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
     }
 
     if (LANE_SPLIT) {
-        for (int off = js >> 1; off > 0; off >>= 1) {
+        for (int off = 16; off >= ipw; off >>= 1) {
 #pragma unroll
             for (int w = 0; w < WPT; ++w) {
                 T other[Op::NA];
@@ -348,8 +354,9 @@ __global__ void __launch_bounds__(NT) pair_kernel_defer(const __grid_constant__ 
 
     const int jsl = LANE_SPLIT ? a.js_log2 : 0;
     const int js = 1 << jsl;
-    const int jsub = tid & (js - 1);
-    const int islot = tid >> jsl;
+    const int ipw = 32 >> jsl;                        // lane layout: see pair_kernel
+    const int jsub = (tid & 31) >> (5 - jsl);
+    const int islot = (tid >> 5) * ipw + (tid & (ipw - 1));
     const int slots = NT >> jsl;
     const long long ibase = (long long)blockIdx.x * slots;
 
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(NT) pair_kernel_defer(const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < NA; ++k) acc[k] = st.acc[k];
     if (LANE_SPLIT) {
-        for (int off = js >> 1; off > 0; off >>= 1) {
+        for (int off = 16; off >= ipw; off >>= 1) {
             T other[NA];
 #pragma unroll
             for (int k = 0; k < NA; ++k) other[k] = __shfl_xor_sync(0xffffffffu, acc[k], off);
