@@ -218,6 +218,9 @@ void tupan_cuda_clear_error(void);
 /* force a launch shape (tests/tuning): lane_split < 0 restores the heuristic */
 void tupan_cuda_force_plan(int lane_split, int js_log2, int jg);
 void tupan_cuda_last_plan(int *lane_split, int *js_log2, int *jg);
+/* the launch shape the cost model picks for `kernel` on ni x nj pairs (no device needed) */
+int tupan_cuda_plan_query(int kernel, long long ni, long long nj, const double *scal, int *lane_split,
+                          int *js_log2, int *jg);
 void tupan_cuda_set_timing(int enable);
 /* stage times of the last call, milliseconds (CUDA events on the stream the call ran on;
  * a device-resident call has no h2d/d2h stage and reports 0 for them) */

@@ -74,6 +74,8 @@ PART2 = {
     "tupan_cuda_clear_error": (None, []),
     "tupan_cuda_force_plan": (None, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "tupan_cuda_last_plan": (None, [ctypes.POINTER(ctypes.c_int)] * 3),
+    "tupan_cuda_plan_query": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]
+                              + [ctypes.POINTER(ctypes.c_int)] * 3),
     "tupan_cuda_set_timing": (None, [ctypes.c_int]),
     "tupan_cuda_last_times": (None, [ctypes.POINTER(ctypes.c_float)] * 5),
     "tupan_cuda_launch_count": (ctypes.c_longlong, []),

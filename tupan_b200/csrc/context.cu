@@ -244,6 +244,22 @@ int tupan_cuda_sweep_slots(int kernel, long long ni, long long rows, const doubl
     if (c.init()) return -1;
     return vt->sweep_slots(ni, rows, scal);
 }
+/* The launch shape choose_plan() gives a kernel for ni x nj pairs.  Needs no device: the model
+ * only uses the SM count (148 until a context is bound to a GPU). */
+int tupan_cuda_plan_query(int kernel, long long ni, long long nj, const double* scal, int* lane_split, int* js_log2,
+                          int* jg)
+{
+    const KernelVTable* vt = vtable(kernel);
+    if (!vt) return -1;
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    const double zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int g = vt->sweep_slots(ni, nj, scal ? scal : zero);
+    if (lane_split) *lane_split = c.last_plan.lane_split;
+    if (js_log2) *js_log2 = c.last_plan.js_log2;
+    if (jg) *jg = c.last_plan.jg;
+    return g > 0 ? 0 : -1;
+}
 int tupan_cuda_sweep_dev(int kernel, long long ni, const void* const* iarr, const void* packed, long long j0,
                          long long j1, const double* scal, void* partial, int slot0, void* stream)
 {

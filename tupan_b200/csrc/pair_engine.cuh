@@ -510,26 +510,6 @@ template <class Op> struct Tune {
     enum { NT = 256, TJ = 128, STAGES = 4, NT_SPLIT = 128 };
 };
 
-// CTAs of the throughput kernel the chip holds at once (occupancy x SMs), cached per Op.
-template <class Op>
-inline int throughput_slots(const DeviceInfo& dev)
-{
-    typedef Tune<Op> U;
-    static int occ = 0;
-    if (occ == 0) {
-        auto k = KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES>();
-        const size_t smem = PairSmemDefer<Op, U::NT, U::TJ, U::STAGES>::BYTES;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, U::NT, smem) != cudaSuccess || n < 1) {
-            cudaGetLastError();
-            n = 1;
-        }
-        occ = n;
-    }
-    return occ * dev.sm_count;
-}
-
 // Issue cost of one pair on the kernel's main pipe, in warp instructions (FP64 or FP32); the
 // launch-plan model below only needs it to within ~20 %.  Specialised next to each Op.
 template <class Op> struct OpCost { enum { value = 32 }; };
@@ -596,7 +576,7 @@ inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
             const double chain = rows_per_lane * lat;
             // every CTA walks the same tiles at the same time: the more of them (and the fewer rows a
             // lane takes from each), the longer the hand-over of a tile
-            const double per_tile = 0.3 + ctas / 1000.0 + 0.15 * js;
+            const double per_tile = 0.3 + ctas / 1000.0 + 0.04 * js;
             const double t = 13.0 + 0.3 * js + (per_sm - 1.0) + (pipe > chain ? pipe : chain) / clk_per_us
                              + per_tile * tpc + finalize_us(g);
             if (t < best) { best = t; best_plan.lane_split = 1; best_plan.js_log2 = js; best_plan.jg = (int)g; }

@@ -140,7 +140,12 @@ template <class Op> struct Runner {
         if (nj > 0) ctx().launches++;
         return 0;
     }
-    static int sweep_slots(long long ni, long long rows) { return plan_for(ni, rows).jg; }
+    static int sweep_slots(long long ni, long long rows)
+    {
+        const Plan p = plan_for(ni, rows);
+        ctx().last_plan = p;          // readable through tupan_cuda_last_plan (plan queries, tests)
+        return p.jg;
+    }
     static int sweep(int n_in, long long ni, const T* const* di, const T* packed, long long j0, long long j1,
                      const typename Op::Params& prm, T* partial, int slot0, cudaStream_t s)
     {
