@@ -270,6 +270,19 @@ int tupan_cuda_hermite_predict_dev(int order, long long n, void *const *rv, void
 int tupan_cuda_hermite_correct_dev(int order, long long n, void *const *rv, void *const *rv0,
                                    const void *const *d0, const void *const *d1, const void *d_ctl,
                                    void *stream);
+/* Individual block time-steps (the reference has none: its adaptive Hermite
+ * moves every particle with the shared minimum block step, integrator/hermite.py:343-401).
+ * order 4 or 6.  block_predict: Taylor prediction of ALL n particles from their own time[i] to
+ * t_next; state = {r v a j [s]} as 3 arrays each (12 or 15), pred = {r v [a j]} (6 or 12: order 6
+ * also needs a, j of the j-particles for snap_crackle).  block_correct: the Hermite corrector of
+ * hermite.py:93-121,160-196 for the n ACTIVE particles (compact arrays), each with its own step
+ * tau[i]; rv0 / d0 = state and derivatives at the start of the particle's step, d1 = derivatives
+ * at the block time, rv = corrected {r v} out. */
+int tupan_cuda_block_predict_dev(int order, long long n, const void *const *state, const void *time,
+                                 double t_next, void *const *pred, void *stream);
+int tupan_cuda_block_correct_dev(int order, long long n, const void *tau, const void *const *rv0,
+                                 const void *const *d0, const void *const *d1, void *const *rv,
+                                 void *stream);
 /* y[k] += x[k] * REAL(c_inner * (c_outer * tau)), k < narr <= 6; tau = ctl[TAU] (1 if d_ctl
  * is NULL).  Replaces drift_n / kick_n (integrator/sia.py:64-84), the half drifts and the
  * += (dr, dv) of sakura_step (integrator/sakura.py:25-48). */

@@ -86,6 +86,11 @@ PART2 = {
     "tupan_cuda_real_bytes": (ctypes.c_int, []),
     # Part 3: O(N) integrator updates on device-resident state
     "tupan_cuda_step_begin_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_block_predict_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]),
+    "tupan_cuda_block_correct_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p]),
     "tupan_cuda_hermite_predict_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                       ctypes.c_void_p]),

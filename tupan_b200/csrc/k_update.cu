@@ -165,6 +165,90 @@ __global__ void __launch_bounds__(256) hermite_correct_kernel(const HermiteRefs 
 }
 
 // ---------------------------------------------------------------------------------------
+// Individual block time-steps (absent from the reference, whose adaptive
+// Hermite advances every particle with the shared minimum block step, hermite.py:343-401).
+// Every particle carries its own time and power-of-two step.  block_predict brings ALL particles
+// to the next block time (Taylor series of the derivatives they hold, Horner form); the force
+// kernels then run rectangular -- active particles against everybody's predicted state --, and
+// block_correct applies the Hermite corrector (the same hermite_corr<ND> as above) to the active
+// ones, each with its own step.
+//   state[3*k + c]: k = 0 r, 1 v, 2 a, 3 j, 4 s  (ND + 2 levels, component c)
+//   pred [3*m + c]: m = 0 r, 1 v and, for ND >= 3 (snap_crackle needs them), 2 a, 3 j
+// ---------------------------------------------------------------------------------------
+struct BlockPredictRefs {
+    const real_t* x[15];
+    real_t* p[12];
+    const real_t* time;
+    double t_next;
+    long long n;
+};
+
+template <int ND>
+__global__ void __launch_bounds__(256) block_predict_kernel(const BlockPredictRefs a)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    constexpr int NL = ND + 2;                  // levels held: r v a j (s)
+    constexpr int NP = ND >= 3 ? 4 : 2;         // levels predicted
+    const real_t dt = (real_t)(a.t_next - (double)a.time[i]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        real_t L[NL];
+#pragma unroll
+        for (int k = 0; k < NL; ++k) L[k] = a.x[3 * k + c][i];
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+            real_t x = L[NL - 1];
+#pragma unroll
+            for (int k = NL - 1; k > m; --k) x = x * dt / (real_t)(k - m) + L[k - 1];
+            a.p[3 * m + c][i] = x;
+        }
+    }
+}
+
+struct BlockCorrectRefs {
+    const real_t* tau;       // per active particle
+    const real_t* rv0[6];    // state at the start of the particle's own step
+    const real_t* d0[9];     // its derivatives there: a j (s)
+    const real_t* d1[9];     // derivatives at the block time
+    real_t* rv[6];           // corrected state out
+    long long n;
+};
+
+template <int ND>
+__global__ void __launch_bounds__(256) block_correct_kernel(const BlockCorrectRefs a)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const real_t tau = a.tau[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const real_t r0 = a.rv0[c][i], v0 = a.rv0[3 + c][i];
+        real_t p0[ND + 1], p1[ND + 1];
+        p0[0] = v0;
+        p1[0] = v0;
+#pragma unroll
+        for (int q = 0; q < ND; ++q) {
+            p0[q + 1] = a.d0[3 * q + c][i];
+            p1[q + 1] = a.d1[3 * q + c][i];
+        }
+        const real_t v1 = hermite_corr<ND>(p0, p1, tau);
+        real_t q0[ND + 1], q1[ND + 1];
+        q0[0] = r0;
+        q1[0] = r0;
+        q0[1] = v0;
+        q1[1] = v1;
+#pragma unroll
+        for (int q = 1; q < ND; ++q) {
+            q0[q + 1] = p0[q];
+            q1[q + 1] = p1[q];
+        }
+        a.rv[c][i] = hermite_corr<ND>(q0, q1, tau);
+        a.rv[3 + c][i] = v1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // axpy: y[k] += x[k] * REAL(c_inner * (c_outer * tau)), k < narr  (drift, kick, += dr)
 // scale: y[k] = x[k] / REAL(denom)
 // ---------------------------------------------------------------------------------------
@@ -454,6 +538,59 @@ int tupan_cuda_hermite_correct_dev(int order, long long n, void* const* rv, void
                                    const void* const* d1, const void* d_ctl, void* stream)
 {
     return hermite_launch(false, order, n, rv, rv0, d0, d1, d_ctl, stream);
+}
+
+int tupan_cuda_block_predict_dev(int order, long long n, const void* const* state, const void* time, double t_next,
+                                 void* const* pred, void* stream)
+{
+    Context* c;
+    std::lock_guard<std::mutex> lock(ctx().mu);
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if (order != 4 && order != 6) return c->fail(cudaErrorInvalidValue, "block_predict: order 4 or 6");
+    if (n <= 0) return 0;
+    const int nd = order / 2;
+    BlockPredictRefs a;
+    for (int k = 0; k < 15; ++k) a.x[k] = k < 3 * (nd + 2) ? (const real_t*)state[k] : nullptr;
+    for (int k = 0; k < 12; ++k) a.p[k] = k < (nd >= 3 ? 12 : 6) ? (real_t*)pred[k] : nullptr;
+    a.time = (const real_t*)time;
+    a.t_next = t_next;
+    a.n = n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nd == 2) block_predict_kernel<2><<<blocks_for(n), 256, 0, s>>>(a);
+    else block_predict_kernel<3><<<blocks_for(n), 256, 0, s>>>(a);
+    TUPAN_CHECK(cudaGetLastError(), "block_predict_kernel");
+    c->launches++;
+    return 0;
+}
+
+int tupan_cuda_block_correct_dev(int order, long long n, const void* tau, const void* const* rv0, const void* const* d0,
+                                 const void* const* d1, void* const* rv, void* stream)
+{
+    Context* c;
+    std::lock_guard<std::mutex> lock(ctx().mu);
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if (order != 4 && order != 6) return c->fail(cudaErrorInvalidValue, "block_correct: order 4 or 6");
+    if (n <= 0) return 0;
+    const int nd = order / 2;
+    BlockCorrectRefs a;
+    a.tau = (const real_t*)tau;
+    for (int k = 0; k < 6; ++k) {
+        a.rv0[k] = (const real_t*)rv0[k];
+        a.rv[k] = (real_t*)rv[k];
+    }
+    for (int k = 0; k < 9; ++k) {
+        a.d0[k] = k < 3 * nd ? (const real_t*)d0[k] : nullptr;
+        a.d1[k] = k < 3 * nd ? (const real_t*)d1[k] : nullptr;
+    }
+    a.n = n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nd == 2) block_correct_kernel<2><<<blocks_for(n), 256, 0, s>>>(a);
+    else block_correct_kernel<3><<<blocks_for(n), 256, 0, s>>>(a);
+    TUPAN_CHECK(cudaGetLastError(), "block_correct_kernel");
+    c->launches++;
+    return 0;
 }
 
 int tupan_cuda_axpy_dev(int narr, long long n, void* const* y, const void* const* x, double c_outer, double c_inner,
