@@ -283,6 +283,11 @@ int tupan_cuda_block_predict_dev(int order, long long n, const void *const *stat
 int tupan_cuda_block_correct_dev(int order, long long n, const void *tau, const void *const *rv0,
                                  const void *const *d0, const void *const *d1, void *const *rv,
                                  void *stream);
+/* block_quantize: new step of the n particles that arrived at t_next -- the largest power of two
+ * <= ts[i] (tupan's pairwise criterion, tstep_kernel), <= dt_max, <= 2 tau[i] and commensurate
+ * with t_next -- and their new time stamp. */
+int tupan_cuda_block_quantize_dev(long long n, const void *ts, const void *tau, double t_next,
+                                  double dt_max, void *dt_new, void *time_new, void *stream);
 /* y[k] += x[k] * REAL(c_inner * (c_outer * tau)), k < narr <= 6; tau = ctl[TAU] (1 if d_ctl
  * is NULL).  Replaces drift_n / kick_n (integrator/sia.py:64-84), the half drifts and the
  * += (dr, dv) of sakura_step (integrator/sakura.py:25-48). */

@@ -19,17 +19,19 @@ _IN = {"acc_jerk_kernel": ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz"),
 
 
 class OracleOps(object):
+    """Same interface as tupan_b200.block.CudaOps on 2-D numpy arrays (one row per quantity)."""
+
     def __init__(self, kind="oracle"):
         self.lib = load(kind, "float64")
 
-    def upload(self, a):
-        return np.array(a, dtype=np.float64)
+    def rows(self, k, n):
+        return np.zeros((k, n))
+
+    def upload(self, dst_row, a):
+        dst_row[...] = a
 
     def download(self, a):
-        return a
-
-    def full(self, n, value):
-        return np.full(n, float(value))
+        return np.array(a)
 
     def next_time(self, time, dt):
         return float((time + dt).min())
@@ -40,47 +42,31 @@ class OracleOps(object):
     def count(self, idx):
         return int(len(idx))
 
-    def gather(self, a, idx):
-        return np.ascontiguousarray(a[idx])
+    def take(self, block, idx):
+        return np.ascontiguousarray(block[:, idx])
 
-    def scatter(self, a, idx, values):
-        a[idx] = values
+    def put(self, block, idx, src):
+        block[:, idx] = src
 
-    def pow2_floor(self, x):
-        m, e = np.frexp(x)
-        return np.ldexp(np.ones_like(x), e - 1)
-
-    def minimum(self, a, b):
-        return np.minimum(a, b)
-
-    def where(self, c, a, b):
-        return np.where(c, a, b)
-
-    def remainder_is_zero(self, t, d):
-        return np.remainder(np.full_like(d, float(t)), d) == 0
-
-    def force(self, kernel, ips, jps, scalars=()):
+    def force(self, kernel, ips, jps, scalars, out_rows):
         ins = _IN[kernel]
         ni, nj = len(ips[ins[0]]), len(jps[ins[0]])
-        outs = [np.zeros(ni) for _ in range(SIGNATURES[kernel].count("O"))]
+        assert len(out_rows) == SIGNATURES[kernel].count("O")
         args = ([ni] + [np.ascontiguousarray(ips[k]) for k in ins] + [nj]
-                + [np.ascontiguousarray(jps[k]) for k in ins] + list(scalars) + outs)
+                + [np.ascontiguousarray(jps[k]) for k in ins] + list(scalars) + list(out_rows))
         call(self.lib, kernel, "float64", *args)
-        return outs
 
-    def predict(self, order, state, time, t_next):
+    def predict(self, order, state_rows, time, t_next, pred_rows):
         # Taylor series of the levels a particle holds (r v a j [s]), Horner form
         nl = order // 2 + 2
         npred = 4 if order >= 6 else 2
         dt = t_next - time
-        pred = []
         for m in range(npred):
             for c in range(3):
-                x = state[3 * (nl - 1) + c].copy()
+                x = state_rows[3 * (nl - 1) + c].copy()
                 for k in range(nl - 1, m, -1):
-                    x = x * dt / (k - m) + state[3 * (k - 1) + c]
-                pred.append(x)
-        return pred
+                    x = x * dt / (k - m) + state_rows[3 * (k - 1) + c]
+                pred_rows[3 * m + c][...] = x
 
     @staticmethod
     def _corr(nd, p0, p1, tau):
@@ -89,15 +75,21 @@ class OracleOps(object):
         # hermite.py:170-196
         return (((p0[3] + p1[3]) * tau / 12 + (p0[2] - p1[2])) * tau / 5 + (p0[1] + p1[1])) * tau / 2 + p0[0]
 
-    def correct(self, order, tau, rv0, d0, d1):
+    def correct(self, order, tau, rv0, d0, d1, rv):
         nd = order // 2
-        r1, v1 = [], []
         for c in range(3):
             p0 = [rv0[3 + c]] + [d0[3 * q + c] for q in range(nd)]
             p1 = [rv0[3 + c]] + [d1[3 * q + c] for q in range(nd)]
             v = self._corr(nd, p0, p1, tau)
             q0 = [rv0[c], rv0[3 + c]] + p0[1:nd]
             q1 = [rv0[c], v] + p1[1:nd]
-            r1.append(self._corr(nd, q0, q1, tau))
-            v1.append(v)
-        return r1 + v1
+            rv[c][...] = self._corr(nd, q0, q1, tau)
+            rv[3 + c][...] = v
+
+    def quantize(self, ts, tau, t_next, dt_max, dt_new, time_new):
+        m, e = np.frexp(ts)
+        cand = np.minimum(np.ldexp(np.ones_like(ts), e - 1), dt_max)
+        twice = 2.0 * tau
+        up = (cand >= twice) & (np.fmod(np.full_like(tau, float(t_next)), twice) == 0)
+        dt_new[...] = np.where(up, twice, np.minimum(cand, tau))
+        time_new[...] = t_next

@@ -21,9 +21,10 @@ power-of-two step (Makino & Aarseth 1992 block scheme, with tupan's ingredients)
   block time, and at most ``dt_max``.
 
 All particles are synchronous at every multiple of ``dt_max``; ``evolve(t_end)`` stops there.
-The bookkeeping (minimum, active mask, gather / scatter of the active set, step quantisation) is
-O(N) array plumbing done with torch on the device; every O(N_active x N) operation is one of the
-kernels of this library.  ``ops`` is the seam the CPU tests use to run the same driver on numpy
+The bookkeeping (minimum, active mask, gather / scatter of the active set) is O(N) array plumbing
+done with torch on the device -- per-particle quantities are the rows of 2-D tensors, so the active
+subset of a whole state is one ``index_select`` and goes back with one ``index_copy_`` --; the
+arithmetic (prediction, forces, corrector, criterion, step quantisation) is kernels of this library.  ``ops`` is the seam the CPU tests use to run the same driver on numpy
 arrays with the oracle kernels (oracle/block_ops.py).
 """
 import ctypes
@@ -36,7 +37,10 @@ S8 = ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz")
 
 
 class CudaOps(object):
-    """Arrays are torch CUDA tensors; arithmetic is the C ABI of include/libtupan_cuda.h."""
+    """Arrays are torch CUDA tensors; arithmetic is the C ABI of include/libtupan_cuda.h.
+
+    Per-particle quantities live as the ROWS of 2-D tensors, so that taking the active subset of
+    a whole particle state is one ``index_select`` and putting it back one ``index_copy_``."""
 
     def __init__(self, device=None):
         import torch
@@ -47,14 +51,14 @@ class CudaOps(object):
         self.backend = backend
 
     # -- plumbing -------------------------------------------------------------------------
-    def upload(self, a):
-        return self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+    def rows(self, k, n):
+        return self.torch.zeros((k, n), dtype=self.torch.float64, device=self.device)
+
+    def upload(self, dst_row, a):
+        dst_row.copy_(self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)))
 
     def download(self, t):
         return t.cpu().numpy()
-
-    def full(self, n, value):
-        return self.torch.full((n,), float(value), dtype=self.torch.float64, device=self.device)
 
     def next_time(self, time, dt):
         return float((time + dt).min().item())
@@ -65,24 +69,11 @@ class CudaOps(object):
     def count(self, idx):
         return int(idx.numel())
 
-    def gather(self, a, idx):
-        return a.index_select(0, idx)
+    def take(self, block, idx):
+        return block.index_select(1, idx)
 
-    def scatter(self, a, idx, values):
-        a.index_copy_(0, idx, values)
-
-    def pow2_floor(self, x):
-        m, e = self.torch.frexp(x)                       # x = m 2^e, m in [0.5, 1)
-        return self.torch.ldexp(self.torch.ones_like(x), e - 1)
-
-    def minimum(self, a, b):
-        return self.torch.minimum(a, b if hasattr(b, "shape") else self.torch.full_like(a, float(b)))
-
-    def where(self, c, a, b):
-        return self.torch.where(c, a, b)
-
-    def remainder_is_zero(self, t, d):
-        return self.torch.remainder(self.torch.full_like(d, float(t)), d) == 0
+    def put(self, block, idx, src):
+        block.index_copy_(1, idx, src)
 
     # -- arithmetic -----------------------------------------------------------------------
     def _ptrs(self, tensors):
@@ -96,26 +87,29 @@ class CudaOps(object):
             self.backend.check(self.lib, what)
             raise self.backend.TupanCudaError("%s failed with code %d" % (what, rc))
 
-    def force(self, kernel, ips, jps, scalars=()):
-        out = self.dev.run(kernel, ips, jps, scalars)
-        return [out[k] for k in self.dev.KERNEL_OUTPUTS[kernel]]
+    def force(self, kernel, ips, jps, scalars, out_rows):
+        self.dev.run(kernel, ips, jps, scalars, dict(zip(self.dev.KERNEL_OUTPUTS[kernel], out_rows)))
 
-    def predict(self, order, state, time, t_next):
-        n = time.numel()
-        npred = 12 if order >= 6 else 6
-        pred = [self.torch.empty(n, dtype=self.torch.float64, device=self.device) for _ in range(npred)]
-        self._ok(self.lib.tupan_cuda_block_predict_dev(order, n, self._ptrs(state), ctypes.c_void_p(time.data_ptr()),
-                                                       float(t_next), self._ptrs(pred), self._stream()),
-                 "block_predict")
-        return pred
+    def predict(self, order, state_rows, time, t_next, pred_rows):
+        self._ok(self.lib.tupan_cuda_block_predict_dev(order, time.numel(), self._ptrs(state_rows),
+                                                       ctypes.c_void_p(time.data_ptr()), float(t_next),
+                                                       self._ptrs(pred_rows), self._stream()), "block_predict")
 
-    def correct(self, order, tau, rv0, d0, d1):
-        n = tau.numel()
-        rv = [self.torch.empty(n, dtype=self.torch.float64, device=self.device) for _ in range(6)]
-        self._ok(self.lib.tupan_cuda_block_correct_dev(order, n, ctypes.c_void_p(tau.data_ptr()), self._ptrs(rv0),
-                                                       self._ptrs(d0), self._ptrs(d1), self._ptrs(rv),
-                                                       self._stream()), "block_correct")
-        return rv
+    def correct(self, order, tau, rv0, d0, d1, rv):
+        self._ok(self.lib.tupan_cuda_block_correct_dev(order, tau.numel(), ctypes.c_void_p(tau.data_ptr()),
+                                                       self._ptrs(rv0), self._ptrs(d0), self._ptrs(d1),
+                                                       self._ptrs(rv), self._stream()), "block_correct")
+
+    def quantize(self, ts, tau, t_next, dt_max, dt_new, time_new):
+        self._ok(self.lib.tupan_cuda_block_quantize_dev(ts.numel(), ctypes.c_void_p(ts.data_ptr()),
+                                                        ctypes.c_void_p(tau.data_ptr()), float(t_next),
+                                                        float(dt_max), ctypes.c_void_p(dt_new.data_ptr()),
+                                                        ctypes.c_void_p(time_new.data_ptr()), self._stream()),
+                 "block_quantize")
+
+
+def _rows(block):
+    return [block[k] for k in range(block.shape[0])]
 
 
 class BlockHermite(object):
@@ -126,87 +120,83 @@ class BlockHermite(object):
         if order not in (4, 6):
             raise ValueError("order 4 or 6")
         self.eta, self.order, self.dt_max, self.pec = float(eta), int(order), float(dt_max), int(pec)
-        self.ops = ops or CudaOps(device)
-        self.n = int(len(ps.mass))
-        o = self.ops
-        self.st = {k: o.upload(getattr(ps, k)) for k in S8}
-        self.levels = (R3, V3, A3, J3) + ((S3,) if order >= 6 else ())     # what a particle holds
-        self.time = o.full(self.n, t0)
+        self.ops = o = ops or CudaOps(device)
+        self.n = n = int(len(ps.mass))
+        self.nd = order // 2                                                   # derivative levels: a j (s)
+        levels = (R3, V3, A3, J3) + ((S3,) if order >= 6 else ())             # what a particle holds
+        self.snames = ("mass", "eps2") + tuple(k for lev in levels for k in lev)
+        self.pnames = ("mass", "eps2") + R3 + V3 + (A3 + J3 if order >= 6 else ())
+        self.S = o.rows(len(self.snames), n)          # state at each particle's own time
+        self.P = o.rows(len(self.pnames), n)          # everybody predicted to the current block time
+        self.T = o.rows(2, n)                         # time, dt
+        for k in ("mass", "eps2") + R3 + V3:
+            o.upload(self.S[self.snames.index(k)], getattr(ps, k))
+        for k in ("mass", "eps2"):
+            o.upload(self.P[self.pnames.index(k)], getattr(ps, k))
+        o.upload(self.T[0], np.full(n, float(t0)))
         self.t = float(t0)
         self.block_steps = 0
         self.particle_steps = 0
         self._start()
 
-    # derivative names of this order: a j (s)
-    @property
-    def dnames(self):
-        return tuple(k for lev in self.levels[2:] for k in lev)
+    def _view(self, block, names):
+        return dict(zip(names, _rows(block)))
 
-    def _derivs(self, ips, jps):
-        """a, j (and s) of the i-set against the j-set; both dicts hold mass eps2 r v (+ a j on
-        the j side when order 6 -- the i side gets the a, j just computed)."""
+    def _derivs(self, ips, jps, d1, scratch):
+        """a, j (and s) of the i-set against the j-set into the rows of d1."""
         o = self.ops
-        aj = o.force("acc_jerk_kernel", ips, jps)
-        if self.order < 6:
-            return aj
-        ii = dict(ips)
-        ii.update(zip(A3 + J3, aj))
-        sc = o.force("snap_crackle_kernel", ii, jps)
-        return aj + sc[:3]
+        o.force("acc_jerk_kernel", ips, jps, (), _rows(d1)[:6])
+        if self.order >= 6:
+            ii = dict(ips)
+            ii.update(zip(A3 + J3, _rows(d1)[:6]))     # the i side uses the a, j just computed
+            o.force("snap_crackle_kernel", ii, jps, (), _rows(d1)[6:9] + _rows(scratch))
 
     def _start(self):
-        o, st = self.ops, self.st
-        jps = dict(st)
-        aj = o.force("acc_jerk_kernel", st, st)
-        st.update(zip(A3 + J3, aj))
-        if self.order >= 6:
-            sc = o.force("snap_crackle_kernel", st, st)
-            st.update(zip(S3, sc[:3]))
-        ts = o.force("tstep_kernel", {k: st[k] for k in S8}, {k: st[k] for k in S8}, (self.eta,))[0]
-        self.dt = o.minimum(o.pow2_floor(ts), self.dt_max)
-        del jps
+        o, n = self.ops, self.n
+        st = self._view(self.S, self.snames)
+        d1 = self.S[8:8 + 3 * self.nd]
+        scratch = o.rows(3, n)
+        self._derivs(st, st, d1, scratch)
+        ts = o.rows(2, n)
+        o.force("tstep_kernel", st, st, (self.eta,), _rows(ts))
+        # first step: the largest power of two <= criterion and <= dt_max (tau = dt_max/2, t = 0
+        # lets block_quantize go up to dt_max)
+        tau = o.rows(1, n)
+        o.upload(tau[0], np.full(n, self.dt_max / 2))
+        new = o.rows(2, n)
+        o.quantize(ts[0], tau[0], 0.0, self.dt_max, new[1], new[0])
+        o.upload(self.T[1], o.download(new[1]))
 
     def step(self):
         """One block step: returns the number of particles advanced."""
-        o, st = self.ops, self.st
-        t_next = o.next_time(self.time, self.dt)
-        state = [st[k] for lev in self.levels for k in lev]
-        pred = o.predict(self.order, state, self.time, t_next)
-        pnames = R3 + V3 + (A3 + J3 if self.order >= 6 else ())
-        jps = {"mass": st["mass"], "eps2": st["eps2"]}
-        jps.update(zip(pnames, pred))
-        idx = o.active(self.time, self.dt, t_next)
-        tau = o.gather(self.dt, idx)
-        rv0 = [o.gather(st[k], idx) for k in R3 + V3]
-        d0 = [o.gather(st[k], idx) for k in self.dnames]
-        ips = {k: o.gather(jps[k], idx) for k in S8}
-        d1 = None
+        o, nd = self.ops, self.nd
+        S, P, T = self.S, self.P, self.T
+        t_next = o.next_time(T[0], T[1])
+        o.predict(self.order, _rows(S)[2:], T[0], t_next, _rows(P)[2:])
+        idx = o.active(T[0], T[1], t_next)
+        na = o.count(idx)
+        Sa, Pa, Ta = o.take(S, idx), o.take(P, idx), o.take(T, idx)
+        tau = Ta[1]
+        d1, scratch = o.rows(3 * nd, na), o.rows(3, na)
+        ips, jps = self._view(Pa, self.pnames), self._view(P, self.pnames)
+        rv0, d0 = _rows(Sa)[2:8], _rows(Sa)[8:8 + 3 * nd]
         for _ in range(self.pec):
-            d1 = self._derivs(ips, jps)
-            rv1 = o.correct(self.order, tau, rv0, d0, d1)
-            # the corrected particles replace their predicted selves, as i and as j
-            for k, v in zip(R3 + V3, rv1):
-                o.scatter(jps[k], idx, v)
-                ips[k] = v
+            self._derivs(ips, jps, d1, scratch)
+            o.correct(self.order, tau, rv0, d0, _rows(d1), _rows(Pa)[2:8])
+            # the corrected particles replace their predicted selves in the j-set
+            o.put(P[2:8], idx, Pa[2:8])
             if self.order >= 6:
-                for k, v in zip(A3 + J3, d1[:6]):
-                    o.scatter(jps[k], idx, v)
-        ts = o.force("tstep_kernel", ips, {k: jps[k] for k in S8}, (self.eta,))[0]
-        # largest power of two <= ts, at most 2 tau (and only if the block time allows), <= dt_max
-        cand = o.minimum(o.pow2_floor(ts), self.dt_max)
-        twice = tau * 2.0
-        up = (cand >= twice) & o.remainder_is_zero(t_next, twice)
-        dt_new = o.where(up, twice, o.minimum(cand, tau))
-        for k, v in zip(R3 + V3, rv1):
-            o.scatter(st[k], idx, v)
-        for k, v in zip(self.dnames, d1):
-            o.scatter(st[k], idx, v)
-        o.scatter(self.time, idx, o.full(o.count(idx), t_next))
-        o.scatter(self.dt, idx, dt_new)
+                o.put(P[8:14], idx, d1[0:6])
+        ts, new = o.rows(2, na), o.rows(2, na)
+        o.force("tstep_kernel", ips, jps, (self.eta,), _rows(ts))
+        o.quantize(ts[0], tau, t_next, self.dt_max, new[1], new[0])
+        o.put(S[2:8], idx, Pa[2:8])
+        o.put(S[8:8 + 3 * nd], idx, d1)
+        o.put(T, idx, new)
         self.t = t_next
         self.block_steps += 1
-        self.particle_steps += o.count(idx)
-        return o.count(idx)
+        self.particle_steps += na
+        return na
 
     def evolve(self, t_end):
         """Advance to ``t_end`` (a multiple of dt_max: every particle is synchronous there)."""
@@ -220,16 +210,17 @@ class BlockHermite(object):
         """Write positions, velocities, times and steps back into a host container."""
         o = self.ops
         for k in R3 + V3:
-            getattr(ps, k)[...] = o.download(self.st[k])
-        ps.time[...] = o.download(self.time)
-        ps.tstep[...] = o.download(self.dt)
+            getattr(ps, k)[...] = o.download(self.S[self.snames.index(k)])
+        ps.time[...] = o.download(self.T[0])
+        ps.tstep[...] = o.download(self.T[1])
         return ps
 
     def energies(self):
         """(kinetic, potential) of the synchronous state, phi from the phi kernel."""
-        o, st = self.ops, self.st
-        five = {k: st[k] for k in ("mass", "rx", "ry", "rz", "eps2")}
-        phi = o.download(o.force("phi_kernel", five, five)[0])
+        o = self.ops
+        st = self._view(self.S, self.snames)
+        phi = o.rows(1, self.n)
+        o.force("phi_kernel", st, st, (), _rows(phi))
         m = o.download(st["mass"])
         v2 = sum(o.download(st[k]) ** 2 for k in V3)
-        return float(0.5 * np.sum(m * v2)), float(0.5 * np.sum(m * phi))
+        return float(0.5 * np.sum(m * v2)), float(0.5 * np.sum(m * o.download(phi[0])))

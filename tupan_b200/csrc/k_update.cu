@@ -248,6 +248,26 @@ __global__ void __launch_bounds__(256) block_correct_kernel(const BlockCorrectRe
     }
 }
 
+// New step of the particles that just arrived at block time t_next: the largest power of two
+// not above the criterion ts, at most dt_max, at most twice the old step tau -- and twice only if
+// t_next is a multiple of it (block steps stay commensurate).  Also stamps their new time.
+__global__ void __launch_bounds__(256) block_quantize_kernel(long long n, const real_t* __restrict__ ts,
+                                                             const real_t* __restrict__ tau, double t_next,
+                                                             double dt_max, real_t* __restrict__ dt_new,
+                                                             real_t* __restrict__ time_new)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int e;
+    frexp((double)ts[i], &e);                     // ts = m 2^e, m in [0.5, 1)
+    double cand = ldexp(1.0, e - 1);
+    cand = cand < dt_max ? cand : dt_max;
+    const double old = (double)tau[i], twice = 2.0 * old;
+    const bool up = cand >= twice && fmod(t_next, twice) == 0.0;
+    dt_new[i] = (real_t)(up ? twice : (cand < old ? cand : old));
+    time_new[i] = (real_t)t_next;
+}
+
 // ---------------------------------------------------------------------------------------
 // axpy: y[k] += x[k] * REAL(c_inner * (c_outer * tau)), k < narr  (drift, kick, += dr)
 // scale: y[k] = x[k] / REAL(denom)
@@ -589,6 +609,22 @@ int tupan_cuda_block_correct_dev(int order, long long n, const void* tau, const 
     if (nd == 2) block_correct_kernel<2><<<blocks_for(n), 256, 0, s>>>(a);
     else block_correct_kernel<3><<<blocks_for(n), 256, 0, s>>>(a);
     TUPAN_CHECK(cudaGetLastError(), "block_correct_kernel");
+    c->launches++;
+    return 0;
+}
+
+int tupan_cuda_block_quantize_dev(long long n, const void* ts, const void* tau, double t_next, double dt_max,
+                                  void* dt_new, void* time_new, void* stream)
+{
+    Context* c;
+    std::lock_guard<std::mutex> lock(ctx().mu);
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if (n <= 0) return 0;
+    block_quantize_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(n, (const real_t*)ts, (const real_t*)tau,
+                                                                          t_next, dt_max, (real_t*)dt_new,
+                                                                          (real_t*)time_new);
+    TUPAN_CHECK(cudaGetLastError(), "block_quantize_kernel");
     c->launches++;
     return 0;
 }
