@@ -271,6 +271,8 @@ def run_cuda(args):
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if world > 1 and sk.transport == "p2p":
+        sk.peer.check()                      # a peer barrier that gave up waiting voids the run: fail loudly
     ms = e0.elapsed_time(e1)
     launches = lib.tupan_cuda_launch_count() - launches0
     # pair-kernel time of the last timed step (events recorded by the library on the same stream)

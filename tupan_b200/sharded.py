@@ -93,7 +93,7 @@ class PeerRows(object):
     peers' buffers mapped here (CUDA IPC; one process per GPU on one node)."""
 
     FLAG_BYTES = 256
-    TIMEOUT_S = 20.0
+    TIMEOUT_S = float(__import__("os").environ.get("TUPAN_B200_PEER_TIMEOUT", "20"))   # per barrier wait
 
     def __init__(self, lib, nbytes, group=None):
         self.lib = lib
