@@ -11,7 +11,28 @@ static inline SakuraParams<real_t> sakura_params(const double* s)
     p.flag = (int)s[1];
     return p;
 }
-TUPAN_DEFINE_VTABLE(vt_sakura_raw, SakuraOp<real_t>, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+// one straight-line variant per flag value (as for the PN levels, k_pn.cu)
+typedef SakuraOp<real_t, 1> SakuraP1;
+typedef SakuraOp<real_t, -1> SakuraM1;
+typedef SakuraOp<real_t, 2> SakuraP2;
+typedef SakuraOp<real_t, -2> SakuraM2;
+typedef SakuraOp<real_t, 0> SakuraNone;
+TUPAN_DEFINE_VTABLE(vt_sakura_p1, SakuraP1, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+TUPAN_DEFINE_VTABLE(vt_sakura_m1, SakuraM1, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+TUPAN_DEFINE_VTABLE(vt_sakura_p2, SakuraP2, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+TUPAN_DEFINE_VTABLE(vt_sakura_m2, SakuraM2, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+TUPAN_DEFINE_VTABLE(vt_sakura_none, SakuraNone, "sakura_kernel", 8, 6, 2, 0, sakura_params)
+
+static const KernelVTable* sakura_vtable_for_flag(double flag)
+{
+    switch ((int)flag) {
+        case 1: return &vt_sakura_p1;
+        case -1: return &vt_sakura_m1;
+        case 2: return &vt_sakura_p2;
+        case -2: return &vt_sakura_m2;
+        default: return &vt_sakura_none;
+    }
+}
 
 // Read and reset the count of pairs whose Kepler sub-stepping hit the 2^MAX_DOUBLINGS bound
 // (synchronises the device).  < 0 on a CUDA error.
@@ -35,19 +56,33 @@ static int kepler_limit_check(const char* where)
     return c.last_error;
 }
 
-// sakura: the pair engine entry points, plus the sub-step-limit check on the synchronous path
+// sakura: the pair engine entry points per flag, plus the sub-step-limit check on the synchronous path
 namespace {
+int sakura_rw(const double* s) { return vt_sakura_p1.row_width(s); }
+int sakura_na(const double* s) { return vt_sakura_p1.n_acc(s); }
 int sakura_host(long long ni, const real_t* const* hi, long long nj, const real_t* const* hj, const double* s,
                 real_t* const* ho)
 {
-    int rc = vt_sakura_raw.run_host(ni, hi, nj, hj, s, ho);
+    int rc = sakura_vtable_for_flag(s[1])->run_host(ni, hi, nj, hj, s, ho);
     if (rc) return rc;
     return kepler_limit_check("sakura_kernel");
 }
+int sakura_dev(long long ni, const real_t* const* di, long long nj, const real_t* const* dj, const double* s,
+               real_t* const* dout, cudaStream_t st)
+{ return sakura_vtable_for_flag(s[1])->run_dev(ni, di, nj, dj, s, dout, st); }
+int sakura_pack(long long nj, const real_t* const* dj, const double* s, real_t* packed, cudaStream_t st)
+{ return vt_sakura_p1.pack(nj, dj, s, packed, st); }
+int sakura_slots(long long ni, long long rows, const double* s)
+{ return sakura_vtable_for_flag(s[1])->sweep_slots(ni, rows, s); }
+int sakura_sweep(long long ni, const real_t* const* di, const real_t* packed, long long j0, long long j1,
+                 const double* s, real_t* partial, int slot0, cudaStream_t st)
+{ return sakura_vtable_for_flag(s[1])->sweep(ni, di, packed, j0, j1, s, partial, slot0, st); }
+int sakura_fin(long long ni, const real_t* const* di, const real_t* partial, int nslots, const double* s,
+               real_t* const* dout, cudaStream_t st)
+{ return sakura_vtable_for_flag(s[1])->finalize(ni, di, partial, nslots, s, dout, st); }
 }  // namespace
-extern const KernelVTable vt_sakura = {"sakura_kernel", 8, 6, 2, 0, vt_sakura_raw.row_width, vt_sakura_raw.n_acc,
-                                       sakura_host, vt_sakura_raw.run_dev, vt_sakura_raw.pack,
-                                       vt_sakura_raw.sweep_slots, vt_sakura_raw.sweep, vt_sakura_raw.finalize};
+extern const KernelVTable vt_sakura = {"sakura_kernel", 8, 6, 2, 0, sakura_rw, sakura_na, sakura_host, sakura_dev,
+                                       sakura_pack, sakura_slots, sakura_sweep, sakura_fin};
 
 // kepler_solver_kernel: arrays of 2*pairs bodies; scal = dt.  Device pointers.
 int kepler_run_dev(long long pairs, const real_t* const* din, double dt, real_t* const* dout, cudaStream_t st)

@@ -284,7 +284,11 @@ template <bool FAST, typename T> TUPAN_DEV bool twobody_evolve(T dt, int flag, T
 // sakura -- replaces sakura_kernel (sakura_kernel.c:5-64, core sakura_kernel_common.h:194-243)
 // =======================================================================================
 template <typename T> struct SakuraParams { T dt; int flag; };
-template <typename T> struct SakuraOp {
+// FLAG is a template parameter: with the flag tested at run time inside the pair, the four
+// variants met at a join point and every pair paid ~40 register moves and 6 branches for it
+// (profiles/r01_sakura_defer_ncu_summary.txt: 139 instructions per pair, 66 of them FP64).
+// FLAG = 0 stands for every other value (no-op, as in the reference).
+template <typename T, int FLAG> struct SakuraOp {
     typedef T real;
     typedef SakuraParams<T> Params;
     enum { NI = 8, NJ = 8, NA = 6, NO = 6, WPT = 1, UNROLL = 1 };
@@ -309,7 +313,7 @@ template <typename T> struct SakuraOp {
         const T e2 = s[IE] + row[J8_E2];
         const T m = s[IM] + row[JM];
         State<T> q = p0;
-        if (twobody_evolve<true>(p.dt, p.flag, m, e2, q)) {
+        if (twobody_evolve<true>(p.dt, FLAG, m, e2, q)) {
             const T mu = row[JM] * rcp_fast(m);
             a[0] = fma(mu, q.x - p0.x, a[0]); a[1] = fma(mu, q.y - p0.y, a[1]); a[2] = fma(mu, q.z - p0.z, a[2]);
             a[3] = fma(mu, q.vx - p0.vx, a[3]); a[4] = fma(mu, q.vy - p0.vy, a[4]); a[5] = fma(mu, q.vz - p0.vz, a[5]);
@@ -323,7 +327,7 @@ template <typename T> struct SakuraOp {
     {
         const State<T> p0 = {d[D_X], d[D_Y], d[D_Z], d[D_VX], d[D_VY], d[D_VZ]};
         State<T> q = p0;
-        twobody_evolve<false>(p.dt, p.flag, d[D_M], d[D_E2], q);
+        twobody_evolve<false>(p.dt, FLAG, d[D_M], d[D_E2], q);
         const T mu = d[D_MJ] / d[D_M];
         c[0] = mu * (q.x - p0.x); c[1] = mu * (q.y - p0.y); c[2] = mu * (q.z - p0.z);
         c[3] = mu * (q.vx - p0.vx); c[4] = mu * (q.vy - p0.vy); c[5] = mu * (q.vz - p0.vz);
@@ -336,8 +340,8 @@ template <typename T> struct SakuraOp {
     }
 };
 
-template <typename T> struct Defers<SakuraOp<T>> { enum { value = 1 }; };
-template <typename T> struct OpCost<SakuraOp<T>> { enum { value = 62 }; };
+template <typename T, int FLAG> struct Defers<SakuraOp<T, FLAG>> { enum { value = 1 }; };
+template <typename T, int FLAG> struct OpCost<SakuraOp<T, FLAG>> { enum { value = (FLAG == 2 || FLAG == -2) ? 90 : 62 }; };
 
 // =======================================================================================
 // Two-body Kepler kernel -- replaces kepler_solver_kernel (kepler_solver_kernel.c:5-50).

@@ -333,7 +333,7 @@ __device__ __forceinline__ void deferred_pair(typename Op::real* slot, typename 
 }
 
 template <class Op, int NT, int TJ, int STAGES, bool LANE_SPLIT>
-__global__ void __launch_bounds__(NT) pair_kernel_defer(const __grid_constant__ PairArgs<Op> a)
+__global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant__ PairArgs<Op> a)
 {
     typedef typename Op::real T;
     typedef PairSmemDefer<Op, NT, TJ, STAGES, true> SM;
