@@ -206,6 +206,15 @@ int tupan_cuda_peer_free(void *dptr);
 int tupan_cuda_peer_barrier_dev(void *const *flags, int rank, int world, double timeout_s, void *stream);
 /* barriers that gave up since the last call (synchronises the device) */
 long long tupan_cuda_peer_timeouts(void);
+/* ONE sweep over the packed rows of `nseg` (<= 8) owners, each in its own (peer-mapped) buffer:
+ * seg_ptr[k] holds seg_rows[k] rows.  The kernel walks logical 128-row tiles -- no tile straddles
+ * two owners -- so transfer over NVLink and arithmetic overlap tile by tile inside one launch.
+ * Writes tupan_cuda_sweep_multi_slots(...) accumulator sets starting at slot0. */
+int tupan_cuda_sweep_multi_slots(int kernel, long long ni, int nseg, const long long *seg_rows,
+                                 const double *scal);
+int tupan_cuda_sweep_multi_dev(int kernel, long long ni, const void *const *iarr, int nseg,
+                               const void *const *seg_ptr, const long long *seg_rows, const double *scal,
+                               void *partial, int slot0, void *stream);
 
 /* min over i of |tstep[i]| on the device (the host-side reduction of
  * tupan/particles/body.py:364-368 fused behind tstep); result is written to *d_min. */

@@ -69,6 +69,11 @@ PART2 = {
     "tupan_cuda_peer_barrier_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                                    ctypes.c_void_p]),
     "tupan_cuda_peer_timeouts": (ctypes.c_longlong, []),
+    "tupan_cuda_sweep_multi_slots": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
+                                                    ctypes.c_void_p]),
+    "tupan_cuda_sweep_multi_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_int, ctypes.c_void_p]),
     "tupan_cuda_init": (ctypes.c_int, []),
     "tupan_cuda_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "tupan_cuda_clear_error": (None, []),

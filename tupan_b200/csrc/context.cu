@@ -244,6 +244,29 @@ int tupan_cuda_sweep_slots(int kernel, long long ni, long long rows, const doubl
     if (c.init()) return -1;
     return vt->sweep_slots(ni, rows, scal);
 }
+/* slots a multi-owner sweep writes (the plan is made for the logical rows: whole tiles per owner) */
+int tupan_cuda_sweep_multi_slots(int kernel, long long ni, int nseg, const long long* seg_rows, const double* scal)
+{
+    const KernelVTable* vt = vtable(kernel);
+    if (!vt || !seg_rows) return -1;
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.init()) return -1;
+    return vt->sweep_slots(ni, multi_logical_rows(nseg, seg_rows), scal);
+}
+int tupan_cuda_sweep_multi_dev(int kernel, long long ni, const void* const* iarr, int nseg,
+                               const void* const* seg_ptr, const long long* seg_rows, const double* scal,
+                               void* partial, int slot0, void* stream)
+{
+    const KernelVTable* vt = vtable(kernel);
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    int rc = c.init();
+    if (rc) return rc;
+    if (!vt || !partial || !seg_ptr || !seg_rows) return c.fail(cudaErrorInvalidValue, "sweep_multi arguments");
+    return vt->sweep_multi(ni, (const real_t* const*)iarr, nseg, (const real_t* const*)seg_ptr, seg_rows, scal,
+                           (real_t*)partial, slot0, (cudaStream_t)stream);
+}
 /* The launch shape choose_plan() gives a kernel for ni x nj pairs.  Needs no device: the model
  * only uses the SM count (148 until a context is bound to a GPU). */
 int tupan_cuda_plan_query(int kernel, long long ni, long long nj, const double* scal, int* lane_split, int* js_log2,

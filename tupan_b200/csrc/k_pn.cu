@@ -53,7 +53,10 @@ int pn_sweep(long long ni, const real_t* const* di, const real_t* packed, long l
 int pn_fin(long long ni, const real_t* const* di, const real_t* partial, int nslots, const double* s,
            real_t* const* dout, cudaStream_t st)
 { return pn_vtable_for_order(s[0])->finalize(ni, di, partial, nslots, s, dout, st); }
+int pn_multi(long long ni, const real_t* const* di, int nseg, const real_t* const* sp, const long long* sr,
+             const double* s, real_t* partial, int slot0, cudaStream_t st)
+{ return pn_vtable_for_order(s[0])->sweep_multi(ni, di, nseg, sp, sr, s, partial, slot0, st); }
 }  // namespace
 extern const KernelVTable vt_pnacc = {"pnacc_kernel", 8, 3, 8, 632, pn_rw, pn_na, pn_host, pn_dev,
-                                      pn_pack, pn_slots, pn_sweep, pn_fin};
+                                      pn_pack, pn_slots, pn_sweep, pn_fin, pn_multi};
 }  // namespace tupan

@@ -80,9 +80,12 @@ int sakura_sweep(long long ni, const real_t* const* di, const real_t* packed, lo
 int sakura_fin(long long ni, const real_t* const* di, const real_t* partial, int nslots, const double* s,
                real_t* const* dout, cudaStream_t st)
 { return sakura_vtable_for_flag(s[1])->finalize(ni, di, partial, nslots, s, dout, st); }
+int sakura_multi(long long ni, const real_t* const* di, int nseg, const real_t* const* sp, const long long* sr,
+                 const double* s, real_t* partial, int slot0, cudaStream_t st)
+{ return sakura_vtable_for_flag(s[1])->sweep_multi(ni, di, nseg, sp, sr, s, partial, slot0, st); }
 }  // namespace
 extern const KernelVTable vt_sakura = {"sakura_kernel", 8, 6, 2, 0, sakura_rw, sakura_na, sakura_host, sakura_dev,
-                                       sakura_pack, sakura_slots, sakura_sweep, sakura_fin};
+                                       sakura_pack, sakura_slots, sakura_sweep, sakura_fin, sakura_multi};
 
 // kepler_solver_kernel: arrays of 2*pairs bodies; scal = dt.  Device pointers.
 int kepler_run_dev(long long pairs, const real_t* const* din, double dt, real_t* const* dout, cudaStream_t st)

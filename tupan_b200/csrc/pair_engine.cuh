@@ -78,11 +78,23 @@ __global__ void pack_j_kernel(InRefs<typename Op::real> j, long long nj, typenam
 // ---------------------------------------------------------------------------------------
 // pair_kernel
 // ---------------------------------------------------------------------------------------
+// Rows that live in several buffers (multi-GPU: every owner's packed rows where they were packed,
+// reached through peer mappings).  The sweep then runs over LOGICAL tiles: segment s contributes
+// ceil(rows[s] / TJ) tiles, tile0[] are the prefix sums, and a tile never straddles two segments.
+enum { MAX_SEG = 8 };
+template <typename T> struct Segments {
+    int nseg;                     // 0: one buffer (jpack, j0, j1)
+    int rows[MAX_SEG];
+    int tile0[MAX_SEG + 1];
+    const T* ptr[MAX_SEG];
+};
+
 template <class Op> struct PairArgs {
     typedef typename Op::real T;
     InRefs<T> i;            // caller's i arrays, libtupan.h order
     long long ni;
     const T* jpack;         // packed j rows
+    Segments<T> seg;        // ... or the rows of several owners (then j0 = 0, j1 = logical tiles * TJ)
     long long j0, j1;       // rows [j0, j1) are swept by this launch ...
     long long jchunk;       // ... blockIdx.y takes rows [j0 + y*jchunk, +jchunk)
     int js_log2;            // log2(lanes per i-particle), lane-split variant only
@@ -126,6 +138,25 @@ TUPAN_DEV void load_row(const typename Op::real* p, typename Op::real (&row)[Pac
 #pragma unroll
         for (int c = 0; c < VN; ++c) row[k * VN + c] = e[c];
     }
+}
+
+// Where the tile that starts at (logical) row r0 lives and how many rows it holds.
+template <class Op, int TJ>
+TUPAN_DEV const typename Op::real* locate_tile(const PairArgs<Op>& a, long long r0, long long jhi, int& cnt)
+{
+    constexpr int NJP = Packed<Op>::NJP;
+    if (a.seg.nseg == 0) {
+        const long long rem = jhi - r0;
+        cnt = rem > TJ ? TJ : (int)rem;
+        return a.jpack + r0 * NJP;
+    }
+    const int L = (int)(r0 / TJ);
+    int s = 0;
+    while (s + 1 < a.seg.nseg && L >= a.seg.tile0[s + 1]) ++s;
+    const int off = (L - a.seg.tile0[s]) * TJ;
+    const int rem = a.seg.rows[s] - off;
+    cnt = rem > TJ ? TJ : rem;
+    return a.seg.ptr[s] + (long long)off * NJP;
 }
 
 template <class Op, int NT, int WPT, int TJ, int STAGES, bool LANE_SPLIT>
@@ -177,12 +208,11 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
 
     auto issue = [&](int t) {  // elected thread: start the bulk copy of tile t
         const int s = t % STAGES;
-        const long long r0 = jlo + (long long)t * TJ;
-        long long cnt = jhi - r0;
-        if (cnt > TJ) cnt = TJ;
+        int cnt;
+        const T* src = locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
         const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
         mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(tiles + s * TILE_ELEMS, a.jpack + r0 * NJP, bytes, &full[s]);
+        bulk_g2s(tiles + s * TILE_ELEMS, src, bytes, &full[s]);
     };
     if (tid == 0) {
         for (int t = 0; t < STAGES && t < ntiles; ++t) issue(t);
@@ -192,8 +222,8 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
         const int s = t % STAGES;
         mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
         const T* sj = tiles + s * TILE_ELEMS;
-        long long rem = jhi - (jlo + (long long)t * TJ);
-        const int cnt = rem > TJ ? TJ : (int)rem;
+        int cnt;
+        locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
 
         if (!LANE_SPLIT) {
             if (cnt == TJ) {
@@ -382,14 +412,13 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
     }
     __syncthreads();
 
-    auto issue = [&](int t) {
+    auto issue = [&](int t) {  // elected thread: start the bulk copy of tile t
         const int s = t % STAGES;
-        const long long r0 = jlo + (long long)t * TJ;
-        long long cnt = jhi - r0;
-        if (cnt > TJ) cnt = TJ;
+        int cnt;
+        const T* src = locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
         const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
         mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(tiles + s * TILE_ELEMS, a.jpack + r0 * NJP, bytes, &full[s]);
+        bulk_g2s(tiles + s * TILE_ELEMS, src, bytes, &full[s]);
     };
     if (tid == 0) {
         for (int t = 0; t < STAGES && t < ntiles; ++t) issue(t);
@@ -420,8 +449,8 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
         const int s = t % STAGES;
         mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
         const T* sj = tiles + s * TILE_ELEMS;
-        long long rem = jhi - (jlo + (long long)t * TJ);
-        const int cnt = rem > TJ ? TJ : (int)rem;
+        int cnt;
+        locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
         const int steps = (cnt + js - 1) >> jsl;
         int k = 0;
         while (true) {
@@ -592,13 +621,20 @@ template <class Op>
 inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real>& iarr, long long ni,
                                 const typename Op::real* jpack, long long j0, long long j1,
                                 const typename Op::Params& prm, typename Op::real* partial, int slot0,
-                                const OutRefs<typename Op::real>& out, cudaStream_t stream)
+                                const OutRefs<typename Op::real>& out, cudaStream_t stream,
+                                const Segments<typename Op::real>* seg = nullptr)
 {
     typedef Tune<Op> U;
     PairArgs<Op> a;
     a.i = iarr;
     a.ni = ni;
     a.jpack = jpack;
+    a.seg.nseg = 0;
+    if (seg) {                  // rows of several owners: sweep the logical tiles [0, tile0[nseg])
+        a.seg = *seg;
+        j0 = 0;
+        j1 = (long long)seg->tile0[seg->nseg] * U::TJ;
+    }
     a.j0 = j0;
     a.j1 = j1;
     const long long rows = j1 - j0;

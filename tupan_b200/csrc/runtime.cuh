@@ -97,7 +97,20 @@ struct KernelVTable {
                  const double* scal, real_t* partial, int slot0, cudaStream_t stream);
     int (*finalize)(long long ni, const real_t* const* di, const real_t* partial, int nslots,
                     const double* scal, real_t* const* dout, cudaStream_t stream);
+    // one sweep over the rows of several owners (peer-mapped buffers); slots as sweep_slots(ni, logical rows)
+    int (*sweep_multi)(long long ni, const real_t* const* di, int nseg, const real_t* const* seg_ptr,
+                       const long long* seg_rows, const double* scal, real_t* partial, int slot0,
+                       cudaStream_t stream);
 };
+
+// logical rows of a multi-owner sweep: every owner's rows rounded up to whole 128-row tiles
+inline long long multi_logical_rows(int nseg, const long long* seg_rows)
+{
+    long long tiles = 0;
+    for (int k = 0; k < nseg; ++k)
+        if (seg_rows[k] > 0) tiles += (seg_rows[k] + 127) / 128;
+    return tiles * 128;
+}
 
 const KernelVTable* vtable(int kernel);
 
@@ -155,6 +168,34 @@ template <class Op> struct Runner {
                     "pair sweep");
         if (ni > 0) ctx().launches++;
         ctx().last_plan = p;
+        return 0;
+    }
+    static int sweep_multi(int n_in, long long ni, const T* const* di, int nseg, const T* const* seg_ptr,
+                           const long long* seg_rows, const typename Op::Params& prm, T* partial, int slot0,
+                           cudaStream_t s)
+    {
+        typedef Tune<Op> U;
+        Context& c = ctx();
+        if (nseg < 1 || nseg > MAX_SEG) return c.fail(cudaErrorInvalidValue, "sweep_multi: 1..8 owners");
+        Segments<T> seg;
+        seg.nseg = 0;
+        seg.tile0[0] = 0;
+        for (int k = 0; k < nseg; ++k) {
+            if (seg_rows[k] <= 0) continue;                       // an owner without particles
+            if (seg_rows[k] > 0x7fffffffLL) return c.fail(cudaErrorInvalidValue, "sweep_multi: rows per owner");
+            seg.rows[seg.nseg] = (int)seg_rows[k];
+            seg.ptr[seg.nseg] = seg_ptr[k];
+            seg.tile0[seg.nseg + 1] = seg.tile0[seg.nseg] + (int)((seg_rows[k] + U::TJ - 1) / U::TJ);
+            seg.nseg++;
+        }
+        if (seg.nseg == 0 || ni <= 0) return 0;
+        const long long rows = (long long)seg.tile0[seg.nseg] * U::TJ;
+        Plan p = plan_for(ni, rows);
+        OutRefs<T> none = out_refs(nullptr, 0);
+        TUPAN_CHECK(launch_pairs<Op>(p, in_refs(di, n_in), ni, nullptr, 0, rows, prm, partial, slot0, none, s, &seg),
+                    "pair sweep (multi-owner)");
+        c.launches++;
+        c.last_plan = p;
         return 0;
     }
     static int finalize(int n_in, int n_out, long long ni, const T* const* di, const T* partial, int nslots,
@@ -326,8 +367,11 @@ template <class Op> struct Runner {
     int VT##_fin(long long ni, const real_t* const* di, const real_t* partial, int nslots, const double* s,      \
                  real_t* const* dout, cudaStream_t st)                                                            \
     { return R_##VT::finalize(N_IN, N_OUT, ni, di, partial, nslots, MAKEPRM(s), dout, st); }                      \
+    int VT##_multi(long long ni, const real_t* const* di, int nseg, const real_t* const* sp,                     \
+                   const long long* sr, const double* s, real_t* partial, int slot0, cudaStream_t st)            \
+    { return R_##VT::sweep_multi(N_IN, ni, di, nseg, sp, sr, MAKEPRM(s), partial, slot0, st); }                   \
     }                                                                                                             \
     extern const KernelVTable VT = {NAME,      N_IN,      N_OUT,     N_SCAL,     FLOPS,      VT##_rw,  VT##_na,   \
-                                    VT##_host, VT##_dev,  VT##_pack, VT##_slots, VT##_sweep, VT##_fin};
+                                    VT##_host, VT##_dev,  VT##_pack, VT##_slots, VT##_sweep, VT##_fin, VT##_multi};
 
 }  // namespace tupan

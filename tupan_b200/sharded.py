@@ -81,6 +81,20 @@ class CudaEngine(object):
                                                ctypes.c_void_p(partial.data_ptr()), slot0, self._stream()),
                  "sweep")
 
+    def sweep_multi_slots(self, kernel, ni, seg_rows, scal):
+        rows = (ctypes.c_longlong * len(seg_rows))(*seg_rows)
+        return self.lib.tupan_cuda_sweep_multi_slots(backend.KERNEL_IDS[kernel], ni, len(seg_rows), rows,
+                                                     scal_array(scal))
+
+    def sweep_multi(self, kernel, it, seg_ptrs, seg_rows, scal, partial, slot0):
+        """One launch over the packed rows of several owners (raw device addresses)."""
+        ptrs = (ctypes.c_void_p * len(seg_ptrs))(*seg_ptrs)
+        rows = (ctypes.c_longlong * len(seg_rows))(*seg_rows)
+        self._ok(self.lib.tupan_cuda_sweep_multi_dev(backend.KERNEL_IDS[kernel], it[0].numel(), self._ptrs(it),
+                                                     len(seg_ptrs), ptrs, rows, scal_array(scal),
+                                                     ctypes.c_void_p(partial.data_ptr()), slot0, self._stream()),
+                 "sweep_multi")
+
     def finalize(self, kernel, it, partial, nslots, scal, ot):
         self._ok(self.lib.tupan_cuda_finalize_dev(backend.KERNEL_IDS[kernel], it[0].numel(), self._ptrs(it),
                                                   ctypes.c_void_p(partial.data_ptr()), nslots,
@@ -252,20 +266,20 @@ class ShardedKernel(object):
         if ni > 0:
             eng.pack(self.kernel, it, scalars, peer.rows[self.rank])
         peer.barrier()                               # every rank's rows are in place
-        # own rows first, then the peers round-robin so that no two ranks pull from the same GPU
+        # ONE launch over every owner's rows: own rows first, then the peers round-robin so that no
+        # two ranks start on the same GPU; the kernel's TMA ring pulls remote tiles over NVLink while
+        # the previous tiles are being computed
         order = [(self.rank + k) % self.world for k in range(self.world)]
-        segs = [(r, self.bounds[r + 1] - self.bounds[r]) for r in order]
-        segs = [(r, cnt) for (r, cnt) in segs if cnt > 0]
-        nslots = [eng.sweep_slots(self.kernel, ni, cnt, scalars) for (_, cnt) in segs]
+        seg_rows = [self.bounds[r + 1] - self.bounds[r] for r in order]
+        seg_ptrs = [peer.rows[r] for r in order]
+        nslots = eng.sweep_multi_slots(self.kernel, ni, seg_rows, scalars) if ni > 0 else 0
         na = eng.n_acc(self.kernel, scalars)
-        need = sum(nslots) * na * max(ni, 1)
+        need = max(nslots, 1) * na * max(ni, 1)
         if self._partial is None or self._partial.numel() < need:
             self._partial = torch.empty(need, dtype=self.dtype, device=self.device)
-        slot = 0
-        for (r, cnt), ns in zip(segs, nslots):
-            if ni > 0:
-                eng.sweep(self.kernel, it, peer.rows[r], 0, cnt, scalars, self._partial, slot)
-            slot += ns
+        if ni > 0:
+            eng.sweep_multi(self.kernel, it, seg_ptrs, seg_rows, scalars, self._partial, 0)
+        slot = nslots
         peer.barrier()                               # everybody is done reading: rows may be repacked
         if ni > 0:
             eng.finalize(self.kernel, it, self._partial, slot, scalars, ot)
