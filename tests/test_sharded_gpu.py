@@ -28,9 +28,12 @@ for n in (5000, 40001):
     for kernel, scal in (("acc_jerk_kernel", ()), ("tstep_kernel", (1.0 / 64,)), ("snap_crackle_kernel", ()),
                          ("phi_kernel", ()), ("sakura_kernel", (1.0 / 1024, 1))):
       # "nccl": all-gather of the packed rows; "p2p": rows read in place through peer mappings
-      for transport in ("nccl", "p2p"):
+      # ... in ONE multi-owner launch (small problems) or one launch per owner (large ones)
+      for transport, multi_max in (("nccl", None), ("p2p", None), ("p2p", 0.0)):
         sk = sharded.ShardedKernel(kernel, n, torch.float64, dev, transport=transport)
         assert sk.transport == transport
+        if multi_max is not None:
+            sk.MULTI_MAX_PAIRS = multi_max
         local = {a: full[a][sk.lo:sk.hi].contiguous() for a in device.KERNEL_INPUTS[kernel]}
         out = sk.evaluate(local, scal)
         out = sk.evaluate(local, scal, out)

@@ -141,11 +141,11 @@ TUPAN_DEV void load_row(const typename Op::real* p, typename Op::real (&row)[Pac
 }
 
 // Where the tile that starts at (logical) row r0 lives and how many rows it holds.
-template <class Op, int TJ>
+template <class Op, int TJ, bool MULTI>
 TUPAN_DEV const typename Op::real* locate_tile(const PairArgs<Op>& a, long long r0, long long jhi, int& cnt)
 {
     constexpr int NJP = Packed<Op>::NJP;
-    if (a.seg.nseg == 0) {
+    if (!MULTI) {
         const long long rem = jhi - r0;
         cnt = rem > TJ ? TJ : (int)rem;
         return a.jpack + r0 * NJP;
@@ -159,7 +159,10 @@ TUPAN_DEV const typename Op::real* locate_tile(const PairArgs<Op>& a, long long 
     return a.seg.ptr[s] + (long long)off * NJP;
 }
 
-template <class Op, int NT, int WPT, int TJ, int STAGES, bool LANE_SPLIT>
+// MULTI = rows in several buffers (Segments); a separate instantiation so that the single-buffer
+// kernel keeps exactly the code (and the 122 registers) it was tuned with -- folding the two
+// cost the headline 3 %.
+template <class Op, int NT, int WPT, int TJ, int STAGES, bool LANE_SPLIT, bool MULTI = false>
 __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairArgs<Op> a)
 {
     typedef typename Op::real T;
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
     auto issue = [&](int t) {  // elected thread: start the bulk copy of tile t
         const int s = t % STAGES;
         int cnt;
-        const T* src = locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
+        const T* src = locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
         const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
         mbar_expect_tx(&full[s], bytes);
         bulk_g2s(tiles + s * TILE_ELEMS, src, bytes, &full[s]);
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
         mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
         const T* sj = tiles + s * TILE_ELEMS;
         int cnt;
-        locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
+        locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
 
         if (!LANE_SPLIT) {
             if (cnt == TJ) {
@@ -362,7 +365,7 @@ __device__ __forceinline__ void deferred_pair(typename Op::real* slot, typename 
     for (int k = 0; k < Op::NA; ++k) slot[k] = c[k];
 }
 
-template <class Op, int NT, int TJ, int STAGES, bool LANE_SPLIT>
+template <class Op, int NT, int TJ, int STAGES, bool LANE_SPLIT, bool MULTI = false>
 __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant__ PairArgs<Op> a)
 {
     typedef typename Op::real T;
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
     auto issue = [&](int t) {  // elected thread: start the bulk copy of tile t
         const int s = t % STAGES;
         int cnt;
-        const T* src = locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
+        const T* src = locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
         const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
         mbar_expect_tx(&full[s], bytes);
         bulk_g2s(tiles + s * TILE_ELEMS, src, bytes, &full[s]);
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
         mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
         const T* sj = tiles + s * TILE_ELEMS;
         int cnt;
-        locate_tile<Op, TJ>(a, jlo + (long long)t * TJ, jhi, cnt);
+        locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
         const int steps = (cnt + js - 1) >> jsl;
         int k = 0;
         while (true) {
@@ -492,10 +495,10 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
 // The kernel an Op runs on: <throughput shape> and <lane split>.
 template <class Op, bool LANE_SPLIT> struct KernelOf {
     typedef void (*Fn)(const PairArgs<Op>);
-    template <int NT, int TJ, int STAGES> static Fn get()
+    template <int NT, int TJ, int STAGES, bool MULTI = false> static Fn get()
     {
-        if constexpr (Defers<Op>::value != 0) return pair_kernel_defer<Op, NT, TJ, STAGES, LANE_SPLIT>;
-        else return pair_kernel<Op, NT, LANE_SPLIT ? 1 : Op::WPT, TJ, STAGES, LANE_SPLIT>;
+        if constexpr (Defers<Op>::value != 0) return pair_kernel_defer<Op, NT, TJ, STAGES, LANE_SPLIT, MULTI>;
+        else return pair_kernel<Op, NT, LANE_SPLIT ? 1 : Op::WPT, TJ, STAGES, LANE_SPLIT, MULTI>;
     }
 };
 
@@ -650,25 +653,28 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
     if (ni <= 0) return cudaSuccess;
     int dev_id = 0;
     cudaGetDevice(&dev_id);
-    if (!plan.lane_split) {
-        auto k = KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES>();
-        const size_t smem = PairSmemDefer<Op, U::NT, U::TJ, U::STAGES>::BYTES;
-        static int attr_device = -1;             // function attributes are per device
-        if (attr_device != dev_id) {
+    const bool multi = seg != nullptr;
+    // function attributes are per device and per instantiation
+    static int attr_device[4] = {-1, -1, -1, -1};
+    auto prepare = [&](typename KernelOf<Op, false>::Fn k, size_t smem, int which) {
+        if (attr_device[which] != dev_id) {
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_device = dev_id;
+            attr_device[which] = dev_id;
         }
+    };
+    if (!plan.lane_split) {
+        auto k = multi ? KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, true>()
+                       : KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, false>();
+        const size_t smem = PairSmemDefer<Op, U::NT, U::TJ, U::STAGES>::BYTES;
+        prepare(k, smem, multi ? 1 : 0);
         const long long per_cta = (long long)U::NT * Op::WPT;
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
         k<<<grid, U::NT, smem, stream>>>(a);
     } else {
-        auto k = KernelOf<Op, true>::template get<U::NT_SPLIT, U::TJ, U::STAGES>();
+        auto k = multi ? KernelOf<Op, true>::template get<U::NT_SPLIT, U::TJ, U::STAGES, true>()
+                       : KernelOf<Op, true>::template get<U::NT_SPLIT, U::TJ, U::STAGES, false>();
         const size_t smem = PairSmemDefer<Op, U::NT_SPLIT, U::TJ, U::STAGES>::BYTES;
-        static int attr_device = -1;
-        if (attr_device != dev_id) {
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_device = dev_id;
-        }
+        prepare(k, smem, multi ? 3 : 2);
         const long long per_cta = (long long)(U::NT_SPLIT >> plan.js_log2);
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
         k<<<grid, U::NT_SPLIT, smem, stream>>>(a);

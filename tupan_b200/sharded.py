@@ -88,7 +88,7 @@ class CudaEngine(object):
 
     def sweep_multi(self, kernel, it, seg_ptrs, seg_rows, scal, partial, slot0):
         """One launch over the packed rows of several owners (raw device addresses)."""
-        ptrs = (ctypes.c_void_p * len(seg_ptrs))(*seg_ptrs)
+        ptrs = (ctypes.c_void_p * len(seg_ptrs))(*[p if isinstance(p, int) else p.data_ptr() for p in seg_ptrs])
         rows = (ctypes.c_longlong * len(seg_rows))(*seg_rows)
         self._ok(self.lib.tupan_cuda_sweep_multi_dev(backend.KERNEL_IDS[kernel], it[0].numel(), self._ptrs(it),
                                                      len(seg_ptrs), ptrs, rows, scal_array(scal),
@@ -182,8 +182,13 @@ class ShardedKernel(object):
     OVERLAP_MIN_PAIRS = 2.0e9      # ~4 ms of acc_jerk fp64 on a B200
     MAX_ROW_WIDTH = 16             # reals per packed row, widest kernel (snap_crackle: 14, padded)
 
+    # peer transport: below this many pairs per rank the owners' rows are swept in ONE launch (the
+    # multi-owner kernel; launch- and tail-bound regime), above it with one launch per owner (the
+    # single-buffer kernel is 3-4 % faster per pair: 1000 vs 958 Gpair/s at N = 2^20 on 2 GPUs)
+    MULTI_MAX_PAIRS = 2.0e10
+
     def __init__(self, kernel, n_total, dtype=torch.float64, device="cuda", group=None, engine=None,
-                 overlap=True, transport=None):
+                 overlap=True, transport=None, peer=None):
         self.kernel = kernel
         self.n = int(n_total)
         self.group = group
@@ -209,7 +214,9 @@ class ShardedKernel(object):
             raise ValueError("transport must be 'nccl' or 'p2p'")
         if self.world == 1 or not self.on_cuda:
             self.transport = "nccl"
-        self.peer = None
+        self.peer = peer               # injected by the CPU tests (rows gathered with gloo behind the same seam)
+        if peer is not None:
+            self.transport = "p2p"
 
     # rows of rank r live at [r * rows_max, r * rows_max + count_r) of the gathered buffer
     def segments(self, split_local=True):
@@ -266,20 +273,31 @@ class ShardedKernel(object):
         if ni > 0:
             eng.pack(self.kernel, it, scalars, peer.rows[self.rank])
         peer.barrier()                               # every rank's rows are in place
-        # ONE launch over every owner's rows: own rows first, then the peers round-robin so that no
-        # two ranks start on the same GPU; the kernel's TMA ring pulls remote tiles over NVLink while
-        # the previous tiles are being computed
+        # own rows first, then the peers round-robin so that no two ranks start on the same GPU; the
+        # kernel's TMA ring pulls remote tiles over NVLink while the previous tiles are computed
         order = [(self.rank + k) % self.world for k in range(self.world)]
         seg_rows = [self.bounds[r + 1] - self.bounds[r] for r in order]
         seg_ptrs = [peer.rows[r] for r in order]
-        nslots = eng.sweep_multi_slots(self.kernel, ni, seg_rows, scalars) if ni > 0 else 0
+        one_launch = float(ni) * self.n < self.MULTI_MAX_PAIRS
+        if ni <= 0:
+            nslots = []
+        elif one_launch:
+            nslots = [eng.sweep_multi_slots(self.kernel, ni, seg_rows, scalars)]
+        else:
+            nslots = [eng.sweep_slots(self.kernel, ni, cnt, scalars) if cnt > 0 else 0 for cnt in seg_rows]
         na = eng.n_acc(self.kernel, scalars)
-        need = max(nslots, 1) * na * max(ni, 1)
+        need = max(sum(nslots), 1) * na * max(ni, 1)
         if self._partial is None or self._partial.numel() < need:
             self._partial = torch.empty(need, dtype=self.dtype, device=self.device)
-        if ni > 0:
+        slot = 0
+        if ni > 0 and one_launch:
             eng.sweep_multi(self.kernel, it, seg_ptrs, seg_rows, scalars, self._partial, 0)
-        slot = nslots
+            slot = nslots[0]
+        elif ni > 0:
+            for ptr, cnt, ns in zip(seg_ptrs, seg_rows, nslots):
+                if cnt > 0:
+                    eng.sweep(self.kernel, it, ptr, 0, cnt, scalars, self._partial, slot)
+                slot += ns
         peer.barrier()                               # everybody is done reading: rows may be repacked
         if ni > 0:
             eng.finalize(self.kernel, it, self._partial, slot, scalars, ot)
