@@ -365,6 +365,9 @@ __device__ __forceinline__ void deferred_pair(typename Op::real* slot, typename 
     for (int k = 0; k < Op::NA; ++k) slot[k] = c[k];
 }
 
+// __launch_bounds__(NT, 2): with (NT) alone ptxas settled for 80 registers and spilled inside
+// sweep_rows to reach three CTAs per SM -- 147 -> 84 Gpair/s for sakura flag 1; two CTAs with 128
+// registers and no spill in the hot function is the better trade.
 template <class Op, int NT, int TJ, int STAGES, bool LANE_SPLIT, bool MULTI = false>
 __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant__ PairArgs<Op> a)
 {
