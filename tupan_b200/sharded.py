@@ -23,6 +23,7 @@ gather / slot bookkeeping can be tested on CPU with the gloo backend:
 * ``group``   -- a torch.distributed process group (nccl on GPUs, gloo in the CPU tests).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -107,7 +108,7 @@ class PeerRows(object):
     peers' buffers mapped here (CUDA IPC; one process per GPU on one node)."""
 
     FLAG_BYTES = 256
-    TIMEOUT_S = float(__import__("os").environ.get("TUPAN_B200_PEER_TIMEOUT", "20"))   # per barrier wait
+    TIMEOUT_S = float(os.environ.get("TUPAN_B200_PEER_TIMEOUT", "20"))   # seconds a barrier waits for a peer
 
     def __init__(self, lib, nbytes, group=None):
         self.lib = lib
@@ -208,7 +209,6 @@ class ShardedKernel(object):
         self._width = None
         # "nccl": all-gather of the packed rows; "p2p": rows stay where they were packed and are
         # read through peer mappings (GPUs of one node only)
-        import os
         self.transport = transport or os.environ.get("TUPAN_B200_TRANSPORT", "nccl")
         if self.transport not in ("nccl", "p2p"):
             raise ValueError("transport must be 'nccl' or 'p2p'")
