@@ -312,6 +312,10 @@ template <typename T, int FLAG> struct SakuraOp {
         p0.vx = s[IVX] - row[J8_VX]; p0.vy = s[IVY] - row[J8_VY]; p0.vz = s[IVZ] - row[J8_VZ];
         const T e2 = s[IE] + row[J8_E2];
         const T m = s[IM] + row[JM];
+        // d is written on BOTH paths: left untouched on the common one it is a loop-carried value for
+        // the compiler, and every pair paid 36 register moves to keep the previous (dead) copy alive
+        d[D_X] = p0.x; d[D_Y] = p0.y; d[D_Z] = p0.z; d[D_VX] = p0.vx; d[D_VY] = p0.vy; d[D_VZ] = p0.vz;
+        d[D_M] = m; d[D_E2] = e2; d[D_MJ] = row[JM];
         State<T> q = p0;
         if (twobody_evolve<true>(p.dt, FLAG, m, e2, q)) {
             const T mu = row[JM] * rcp_fast(m);
@@ -319,8 +323,6 @@ template <typename T, int FLAG> struct SakuraOp {
             a[3] = fma(mu, q.vx - p0.vx, a[3]); a[4] = fma(mu, q.vy - p0.vy, a[4]); a[5] = fma(mu, q.vz - p0.vz, a[5]);
             return false;
         }
-        d[D_X] = p0.x; d[D_Y] = p0.y; d[D_Z] = p0.z; d[D_VX] = p0.vx; d[D_VY] = p0.vy; d[D_VZ] = p0.vz;
-        d[D_M] = m; d[D_E2] = e2; d[D_MJ] = row[JM];
         return true;
     }
     static TUPAN_DEV void pair_slow(const T (&d)[ND], const Params& p, T (&c)[NA])
