@@ -50,6 +50,7 @@ METRIC = "acc_jerk pair-interactions/s fp64"
 # re-reads the i-state and writes a partial accumulator slot); at 1.3 GB/s it is 0.02 % of HBM
 # bandwidth -- this kernel is FP64-pipe bound.
 NCU_TRAFFIC = {(1 << 20, 1): 1567549000 + 1357939000}
+NCU_TRAFFIC_CHUNKS = 25      # the capture was taken with the j range in 25 chunks
 
 
 def parse():
@@ -326,7 +327,15 @@ def run_cuda(args):
     nominal_tf = sm_count * 64 * 2 * 1965e6 * 1e-12
     roofline = {
         "bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf, "traffic": NCU_TRAFFIC.get((n, world)),
+        "frac": achieved_tf / peak_tf,
+        # only quoted for the launch shape it was captured with; otherwise null + the note below
+        "traffic": NCU_TRAFFIC.get((n, world)) if plan[2].value == NCU_TRAFFIC_CHUNKS else None,
+        "traffic_note": "last ncu capture (profiles/r01_accjerk_v4_n1m_ncu_summary.txt, 25 j-chunks): 2.93 GB per "
+                        "launch = accumulator workspace written once and read once (chunks x 6 x 8 MB x 2) on top of "
+                        "the 184.5 MB of algorithmic bytes; the packed rows stay in L2; this run used %d chunks, so "
+                        "about %.1f GB, i.e. %.2f %% of the kernel time at the measured HBM bandwidth"
+                        % (plan[2].value, plan[2].value * 6 * 8 * n / 1e9 * 2 / max(world, 1) + 0.4,
+                           100 * (plan[2].value * 6 * 8 * n * 2 / max(world, 1) + 0.4e9) / 6.5e12 / (kern_ms * 1e-3)),
         "kernel": "pair_kernel<AccJerkOp<double>>", "kernel_ms": kern_ms,
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": local_pairs,
         "peak_source": "measured: pure-DFMA probe in this process (%.2f TFLOP/s = %d SMs x 64 lanes x 2 x %.0f MHz);"
