@@ -334,8 +334,9 @@ def run_cuda(args):
                         "launch = accumulator workspace written once and read once (chunks x 6 x 8 MB x 2) on top of "
                         "the 184.5 MB of algorithmic bytes; the packed rows stay in L2; this run used %d chunks, so "
                         "about %.1f GB, i.e. %.2f %% of the kernel time at the measured HBM bandwidth"
-                        % (plan[2].value, plan[2].value * 6 * 8 * n / 1e9 * 2 / max(world, 1) + 0.4,
-                           100 * (plan[2].value * 6 * 8 * n * 2 / max(world, 1) + 0.4e9) / 6.5e12 / (kern_ms * 1e-3)),
+                        % (plan[2].value, (plan[2].value * 6 * 8 * n * 2 / max(world, 1) + 22 * 8 * n) / 1e9,
+                           100 * (plan[2].value * 6 * 8 * n * 2 / max(world, 1) + 22 * 8 * n) / 6.5e12
+                           / (kern_ms * 1e-3)),
         "kernel": "pair_kernel<AccJerkOp<double>>", "kernel_ms": kern_ms,
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": local_pairs,
         "peak_source": "measured: pure-DFMA probe in this process (%.2f TFLOP/s = %d SMs x 64 lanes x 2 x %.0f MHz);"
