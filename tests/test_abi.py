@@ -38,6 +38,17 @@ def test_library_exports_every_declared_symbol(prec):
     assert backend.load(prec).tupan_cuda_real_bytes() == (8 if prec == "float64" else 4)
 
 
+def test_every_new_entry_point_has_a_ctypes_signature():
+    # Parts 2, 2b, 3, 3b of the header (everything that is not one of the reference's ten functions)
+    # are bound with explicit argument types in backend.PART2: a missing entry would let ctypes guess
+    # int-sized arguments for pointers
+    names = [n for n in declared_functions() if n not in backend.SIGNATURES]
+    missing = [n for n in names if n not in backend.PART2]
+    assert not missing, missing
+    stale = [n for n in backend.PART2 if n not in names]
+    assert not stale, stale
+
+
 def test_signatures_match_oracle_bindings():
     import oracle
     assert oracle.SIGNATURES == backend.SIGNATURES

@@ -57,3 +57,20 @@ def test_equal_steps_reduce_to_one_block():
     b = BlockHermite(1.0 / 16, ps, order=4, dt_max=2.0 ** -6, ops=OracleOps())
     n0 = b.step()
     assert n0 == 4 and b.t == 2.0 ** -6
+
+
+def test_step_quantisation_rules():
+    # block_quantize (csrc/k_update.cu) restated in oracle/block_ops.py: largest power of two <= the
+    # criterion, <= dt_max, at most twice the old step and only when the block time is a multiple of it
+    o = OracleOps()
+    ts = np.array([0.3, 0.25, 0.2499, 1e-3, 5.0, 0.13, 0.13])
+    tau = np.array([0.125, 0.125, 0.125, 0.125, 0.125, 0.03125, 0.03125])
+    dt, tm = np.zeros(7), np.zeros(7)
+    o.quantize(ts, tau, 0.25, 0.25, dt, tm)          # t = 0.25 is a multiple of 0.25 and of 0.0625
+    #   0.3 -> 0.25 = 2 tau, allowed; 0.25 -> 0.25; 0.2499 -> 0.125; 1e-3 -> 2^-10; 5 -> dt_max = 2 tau;
+    #   0.13 with tau = 1/32: candidate 1/8 but only one doubling per step -> 1/16
+    assert np.array_equal(dt, [0.25, 0.25, 0.125, 2.0 ** -10, 0.25, 0.0625, 0.0625])
+    assert np.all(tm == 0.25)
+    o.quantize(ts, tau, 0.375, 0.25, dt, tm)         # 0.375 is NOT a multiple of 0.25: no doubling of 1/8
+    assert np.array_equal(dt[:5], [0.125, 0.125, 0.125, 2.0 ** -10, 0.125])
+    assert np.array_equal(dt[5:], [0.0625, 0.0625])  # 0.375 is a multiple of 1/16
