@@ -18,6 +18,10 @@ reference loop evaluates them) -- one force evaluation of a Hermite step.
                rate this board sustains in a pure-DFMA probe run in the same process.
 * ``cpu_baseline`` the reference's C backend (oracle/_ref, else the oracle port) on the host
                cores, on a bounded i-sample against the full j-set.
+* ``parity``   after the timed region (never inside it) every rank checks the outputs of its LAST
+               timed launch -- and of the last end-to-end call -- on an i-sample of its shard
+               against the reference C backend with the full j-set: per-particle norm-relative
+               error of acc and of jerk, maximum over the sample and over ranks; tolerance 1e-12.
 
 With N > 1 (torchrun, one rank per GPU) the i-set is sharded, the packed j rows are
 all-gathered over NCCL once per step, total work is fixed: "scaling": "strong".
@@ -49,8 +53,17 @@ METRIC = "acc_jerk pair-interactions/s fp64"
 # algorithmic bytes because the j range is split into 25 chunks for wave balance (each chunk
 # re-reads the i-state and writes a partial accumulator slot); at 1.3 GB/s it is 0.02 % of HBM
 # bandwidth -- this kernel is FP64-pipe bound.
-NCU_TRAFFIC = {(1 << 20, 1): 1567549000 + 1357939000}
-NCU_TRAFFIC_CHUNKS = 25      # the capture was taken with the j range in 25 chunks
+# keyed by (n, GPUs, j-chunks of the launch)
+NCU_TRAFFIC = {(1 << 20, 1, 25): 1567549000 + 1357939000}
+KERNEL_NAME = "pair_kernel_grouped<AccJerkOp<double>>"
+PARITY_TOL = 1e-12           # BASELINE.json north_star: ~1e-12 in fp64 (summation order differs)
+PARITY_SAMPLE = 256          # i-particles per rank checked against the full j-set
+
+
+def workload_config(n):
+    """The part of `config` both arms print identically."""
+    return {"workload": "Plummer sphere N=%d equal-mass, eps=4/N, acc_jerk fp64 (one Hermite force "
+                        "evaluation)" % n, "n": n}
 
 
 def parse():
@@ -154,6 +167,33 @@ def cpu_sample_size(n, cores, seconds=4.0, rate_per_core=0.9e8):
     return max(cores, min(n, (ni // cores) * cores))
 
 
+def parity_sample(ps, n, lo, hi, got, lib, cores, nsample=PARITY_SAMPLE):
+    """max over a sample of this shard's particles of ||got - ref|| / ||ref|| (acc and jerk
+    separately), ref = the reference C backend on the same inputs with the full j-set.
+    `got` = six arrays holding the shard's outputs (index 0 = particle lo)."""
+    import oracle
+    ni = hi - lo
+    if ni <= 0:
+        return 0.0, 0
+    k = min(nsample, ni)
+    rng = np.random.default_rng(1234 + lo)
+    idx = np.unique(np.concatenate([np.linspace(0, ni - 1, k // 2).astype(np.int64),
+                                    rng.integers(0, ni, k - k // 2)]))
+    ia = [np.ascontiguousarray(getattr(ps, a)[lo + idx]) for a in S8]
+    ja = [np.ascontiguousarray(getattr(ps, a)) for a in S8]
+    ref = [np.zeros(len(idx)) for _ in range(6)]
+    oracle.call_threaded(lib, "acc_jerk_kernel", "float64", max(1, min(cores, len(idx))),
+                         *([len(idx)] + ia + [n] + ja + ref))
+    worst = 0.0
+    for g0 in (0, 3):
+        g = np.stack([np.asarray(got[g0 + c])[idx] for c in range(3)])
+        r = np.stack(ref[g0:g0 + 3])
+        if not np.all(np.isfinite(g)):
+            return float("inf"), len(idx)
+        worst = max(worst, float(np.max(np.sqrt(((g - r) ** 2).sum(0)) / np.sqrt((r ** 2).sum(0)))))
+    return worst, len(idx)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -176,8 +216,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Plummer sphere N=%d equal-mass, eps=4/N, acc_jerk fp64 (one Hermite force "
-                               "evaluation)" % n, "n": n},
+        "config": workload_config(n),
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
                          "sample": "each step = ni=%d i-particles (evenly spaced) x nj=%d, %d threads on "
                                    "contiguous i-slices of the unmodified C function" % (ni, n, cores)},
@@ -276,10 +315,13 @@ def run_cuda(args):
         sk.peer.check()                      # a peer barrier that gave up waiting voids the run: fail loudly
     ms = e0.elapsed_time(e1)
     launches = lib.tupan_cuda_launch_count() - launches0
-    # pair-kernel time of the last timed step (events recorded by the library on the same stream)
-    tp = [ctypes.c_float() for _ in range(5)]
-    lib.tupan_cuda_last_times(*[ctypes.byref(x) for x in tp])
-    pair_ms = tp[2].value
+    # pair-kernel time: the library records CUDA events around every pair-kernel launch on the
+    # launching stream; summed over ALL launches of the timed region, divided by the steps
+    sums = (ctypes.c_float * 5)()
+    calls = ctypes.c_longlong()
+    wrapped = lib.tupan_cuda_sum_times(sums, ctypes.byref(calls))
+    pair_ms = sums[2] / args.steps if (calls.value > 0 and not wrapped) else 0.0
+    pair_launches_per_step = calls.value / float(args.steps)
     lib.tupan_cuda_set_timing(0)
     plan = [ctypes.c_int() for _ in range(3)]
     lib.tupan_cuda_last_plan(*[ctypes.byref(x) for x in plan])
@@ -289,6 +331,13 @@ def run_cuda(args):
     ms = float(t.item())
     ms_per_step = ms / args.steps
     value = float(n) * n / (ms_per_step * 1e-3)
+
+    # ---- parity of the outputs of the last timed launch (outside the timed region) -------------
+    plib, pkind = cpu_reference_lib()
+    cores = os.cpu_count() or 1
+    got = [out[a].cpu().numpy() for a in OUT6]
+    perr, pn = parity_sample(ps, n, lo, hi, got, plib, max(1, cores // max(1, min(world, 8))))
+    perr_e2e = None
 
     # ---- end to end through the reference-facing API with host arrays --------------------------
     e2e = None
@@ -308,11 +357,25 @@ def run_cuda(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        perr_e2e, _ = parity_sample(ps, n, lo, hi, [getattr(ips, a) for a in OUT6], plib,
+                                    max(1, cores // max(1, min(world, 8))))
         h2d = 8 * ni * 8 + (0 if world == 1 else 8 * n * 8)   # j arrays alias the i arrays at N=1
         e2e = {"value": float(n) * n / (dt / args.steps), "unit": "pairs/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(6 * ni * 8),
                "api": "ParticleSystem.set_acc_jerk -> extensions.AccJerk.calc -> CUDAKernel -> acc_jerk_kernel "
                       "(C ABI, pinned host arrays)"}
+
+    pt = torch.tensor([perr, perr_e2e if perr_e2e is not None else 0.0], dtype=torch.float64, device=dev)
+    pc = torch.tensor([1.0 if pn > 0 else 0.0, float(pn)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pc, op=dist.ReduceOp.SUM)
+    parity = {"max_err": float(pt[0].item()), "e2e_max_err": float(pt[1].item()) if e2e is not None else None,
+              "n_sample": int(pc[1].item()), "ranks_checked": int(pc[0].item()), "tolerance": PARITY_TOL,
+              "oracle": "oracle/_ref (unmodified reference C)" if pkind == "reference" else "oracle port",
+              "what": "outputs of the last timed launch on every rank's shard, i-sample x full j-set, "
+                      "max over particles of ||d acc||/||acc|| and ||d jerk||/||jerk||",
+              "ok": bool(pt.max().item() <= PARITY_TOL)}
 
     if rank != 0:
         if world > 1:
@@ -324,28 +387,46 @@ def run_cuda(args):
     kern_ms = pair_ms if pair_ms > 0 else ms_per_step
     achieved_tf = FLOPS_PER_PAIR * local_pairs / (kern_ms * 1e-3) * 1e-12
     sm_count = lib.tupan_cuda_sm_count()
+    # three denominators: nominal lanes x clock; the best instruction-shape probe
+    # (DADD / DMUL / 2-register DFMA run at the nominal rate); the 3-register DFMA chain probe
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     nominal_tf = sm_count * 64 * 2 * 1965e6 * 1e-12
+    nominal_sampled_tf = sm_count * 64 * 2 * sm_mhz * 1e6 * 1e-12
+    probes = {"dfma_3reg_chain": peak_tf}
+    for kind, name in ((1, "dadd"), (2, "dmul"), (3, "dfma_2reg")):
+        tops = ctypes.c_double()
+        if lib.tupan_cuda_pipe_probe(kind, 100.0, ctypes.byref(tops)) == 0:
+            probes[name] = 2.0 * tops.value       # as TFLOP/s-equivalent: 2 flop per FMA lane
+    best_probe_tf = max(probes.values())
+    algorithmic = int((8 + 6) * ni * 8 + 8 * n * 8)
+    chunks = plan[2].value
+    workspace = (chunks * 6 * 8 * ni * 2) if chunks > 1 else 0
     roofline = {
-        "bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf,
-        # only quoted for the launch shape it was captured with; otherwise null + the note below
-        "traffic": NCU_TRAFFIC.get((n, world)) if plan[2].value == NCU_TRAFFIC_CHUNKS else None,
-        "traffic_note": "last ncu capture (profiles/r01_accjerk_v4_n1m_ncu_summary.txt, 25 j-chunks): 2.93 GB per "
-                        "launch = accumulator workspace written once and read once (chunks x 6 x 8 MB x 2) on top of "
-                        "the 184.5 MB of algorithmic bytes; the packed rows stay in L2; this run used %d chunks, so "
-                        "about %.1f GB, i.e. %.2f %% of the kernel time at the measured HBM bandwidth"
-                        % (plan[2].value, (plan[2].value * 6 * 8 * n * 2 / max(world, 1) + 22 * 8 * n) / 1e9,
-                           100 * (plan[2].value * 6 * 8 * n * 2 / max(world, 1) + 22 * 8 * n) / 6.5e12
-                           / (kern_ms * 1e-3)),
-        "kernel": "pair_kernel<AccJerkOp<double>>", "kernel_ms": kern_ms,
-        "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": local_pairs,
-        "peak_source": "measured: pure-DFMA probe in this process (%.2f TFLOP/s = %d SMs x 64 lanes x 2 x %.0f MHz);"
-                       " MEASURED_PEAKS.json has no FP64 entry; nominal at 1965 MHz = %.1f TFLOP/s"
-                       % (peak_tf, sm_count, peak_mhz, nominal_tf),
+        "bound": "fp64_fma", "achieved": achieved_tf, "peak": nominal_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / nominal_tf,
         "frac_of_nominal": achieved_tf / nominal_tf,
+        "frac_of_nominal_at_sampled_clock": achieved_tf / nominal_sampled_tf,
+        "frac_of_best_probe": achieved_tf / best_probe_tf,
+        "frac_of_dfma_chain_probe": achieved_tf / peak_tf,
+        "peak_probes_tflops": probes,
+        "peak_source": "nominal: %d SMs x 64 FP64 lanes x 2 flop x 1965 MHz = %.2f TFLOP/s (MEASURED_PEAKS.json has "
+                       "no FP64 entry); probes measured in this process: DADD / DMUL / 2-register DFMA reach it, a "
+                       "chain of 3-register DFMAs needs a third clock per instruction (tools/microbench2.cu)"
+                       % (sm_count, nominal_tf),
+        "traffic": NCU_TRAFFIC.get((n, world, chunks)),
+        "traffic_note": "ncu dram bytes are quoted only for the launch shape they were captured with (n, GPUs, "
+                        "j-chunks) = %s; this run: %d chunk(s), accumulator workspace %.2f GB written + read on top "
+                        "of %.1f MB algorithmic, %.3f %% of the kernel time at the measured HBM bandwidth"
+                        % (sorted(NCU_TRAFFIC), chunks, workspace / 1e9, algorithmic / 1e6,
+                           100 * (workspace + algorithmic) / 6.5e12 / (kern_ms * 1e-3)),
+        "kernel": KERNEL_NAME, "kernel_ms": kern_ms,
+        "kernel_ms_what": "mean over the timed steps of the summed pair-kernel launches of a step (%.1f per step), "
+                          "CUDA events on the launching stream" % pair_launches_per_step
+        if pair_ms > 0 else "step time (no per-kernel events)",
+        "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": local_pairs / max(pair_launches_per_step, 1.0),
         "dp_instr_per_pair": DP_INSTR_PER_PAIR,
-        "dp_pipe_frac": DP_INSTR_PER_PAIR * 2 * local_pairs / (kern_ms * 1e-3) * 1e-12 / peak_tf,
-        "algorithmic_bytes": int((8 + 6) * ni * 8 + 8 * n * 8),
+        "dp_pipe_frac": DP_INSTR_PER_PAIR * 2 * local_pairs / (kern_ms * 1e-3) * 1e-12 / nominal_tf,
+        "algorithmic_bytes": algorithmic,
         "hbm_note": "arithmetic intensity ~2.5e5 flop/B: HBM (%.0f GB/s measured) is not the bound"
                     % json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 0)
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "HBM is not the bound",
@@ -370,13 +451,13 @@ def run_cuda(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Plummer sphere N=%d equal-mass, eps=4/N, acc_jerk fp64 (one Hermite force "
-                               "evaluation)" % n, "n": n, "parallelism": "i-shard x%d, %s" % (
-                                   world, "j rows read in place over NVLink (peer mappings)"
-                                   if world > 1 and sk.transport == "p2p" else "j all-gather"),
-                   "l2": "256 MiB buffer written between steps (inside the timed region)",
-                   "plan": {"lane_split": plan[0].value, "js_log2": plan[1].value, "jg": plan[2].value}},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "config": workload_config(n),
+        "run": {"parallelism": "i-shard x%d, %s" % (
+                    world, "j rows read in place over NVLink (peer mappings)"
+                    if world > 1 and sk.transport == "p2p" else "j all-gather"),
+                "l2": "256 MiB buffer written between steps (inside the timed region)",
+                "plan": {"lane_split": plan[0].value, "js_log2": plan[1].value, "jg": plan[2].value}},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
         "roofline": roofline, "cpu_baseline": cpu, "tflops": FLOPS_PER_PAIR * value * 1e-12,
     }
     print(json.dumps(line), flush=True)

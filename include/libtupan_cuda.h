@@ -234,6 +234,11 @@ void tupan_cuda_set_timing(int enable);
 /* stage times of the last call, milliseconds (CUDA events on the stream the call ran on;
  * a device-resident call has no h2d/d2h stage and reports 0 for them) */
 void tupan_cuda_last_times(float *h2d, float *pack, float *pair, float *finalize, float *d2h);
+/* stage times summed over every call since tupan_cuda_set_timing(1) (each call keeps its own CUDA
+ * events, up to 256 calls; bare tupan_cuda_sweep_dev / _multi_dev calls count as calls with a pair
+ * stage only); sums5 = {h2d, pack, pair, finalize, d2h} in ms.  Returns 1 if more than 256 calls
+ * were made (the oldest are then missing from the sums), else 0.  Synchronises the device. */
+int tupan_cuda_sum_times(float *sums5, long long *calls);
 long long tupan_cuda_launch_count(void);           /* kernels launched since load */
 /* kernels of this library replayed from a CUDA graph the caller captured (launches inside a
  * capture are counted once, at capture time; the caller adds them per replay) */
@@ -241,6 +246,11 @@ void tupan_cuda_count_launches(long long n);
 int tupan_cuda_sm_count(void);
 /* FMA-pipe micro-benchmark in the library's precision: sustained TFLOP/s over `ms` ms */
 int tupan_cuda_fma_peak(double ms, double *tflops, double *sm_mhz_effective);
+/* The other instruction shapes of the same pipe: kind 1 = x + y, 2 = x * y, 3 = fma(x, y, 1)
+ * (two register operands + immediate); result in 1e12 instructions x lanes per second (an FMA
+ * counts 2 flop).  On a B200 these run at the nominal 64 lanes/clk/SM in fp64, while the 3-register
+ * chains of tupan_cuda_fma_peak need a third clock per instruction to collect their operands. */
+int tupan_cuda_pipe_probe(int kind, double ms, double *tera_ops);
 int tupan_cuda_real_bytes(void);                   /* sizeof(REAL): 8 or 4 */
 
 /* ------------------------------------------------------------------------------------ */

@@ -1,0 +1,114 @@
+"""GPU parity at the BENCHED configuration and launch shapes ("no parity at the
+benched configuration"): BASELINE.json's headline is acc_jerk fp64 at N = 2^20, which the launch
+plan runs as a 2-D grid of i-blocks x j-chunks (raw accumulators in a workspace, then
+finalize_kernel) -- a shape the small-N tests only reach with 2-5 chunks.
+
+* sampled parity at N = 2^20 with the automatic plan (the oracle on 256 i-particles x the full
+  j-set, tolerance 1e-12 as everywhere, test_parity_gpu.py);
+* forced plans with 32 and 64 j-chunks at small N, every Newtonian kernel;
+* rectangular ni = 65536 x nj = 4194304 (the i-sharded shape of an 8-GPU run at N = 4M, and the
+  shape block time-steps produce);
+* size-independent properties at full size: Newton's third law for the jerk and the
+  acceleration (sum_i m_i a_i = 0, sum_i m_i j_i = 0)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from util import KERNELS, S8, as_dict, cuda_lib, cuda_run, rel_err, run
+from tupan_b200 import backend, ics
+
+pytestmark = pytest.mark.gpu
+CORES = os.cpu_count() or 1
+
+
+@pytest.fixture(autouse=True)
+def _auto_plan():
+    yield
+    for prec in ("float64", "float32"):
+        backend.load(prec).tupan_cuda_force_plan(-1, 0, 1)
+
+
+def reference_lib(prec="float64"):
+    """The unmodified reference C backend when it was built here (oracle/_ref), else its pinned
+    restatement (bit-identical to it, tests/test_oracle.py)."""
+    return oracle.load("ref" if oracle.have("ref", prec) else "oracle", prec)
+
+
+def oracle_sample(name, data, idx, scalars=None, prec="float64"):
+    attrs, default, _ = KERNELS[name]
+    scalars = default if scalars is None else scalars
+    n = len(data["mass"])
+    ia = [np.ascontiguousarray(data[a][idx]) for a in attrs]
+    ja = [np.ascontiguousarray(data[a]) for a in attrs]
+    outs = [np.zeros(len(idx), np.dtype(prec)) for _ in range(oracle.n_outputs(name))]
+    oracle.call_threaded(reference_lib(prec), name, prec, CORES, *([len(idx)] + ia + [n] + ja + list(scalars) + outs))
+    return outs
+
+
+def last_plan(lib):
+    p = [ctypes.c_int() for _ in range(3)]
+    lib.tupan_cuda_last_plan(*[ctypes.byref(x) for x in p])
+    return tuple(x.value for x in p)
+
+
+def test_acc_jerk_sampled_parity_at_n_2_20():
+    n = 1 << 20
+    ps = ics.make_plummer(n, seed=1)                       # the bench's system
+    data = as_dict(ps, "float64")
+    lib = cuda_lib("float64")
+    got = cuda_run("acc_jerk_kernel", "float64", data, data)
+    lane_split, _, jg = last_plan(lib)
+    assert lane_split == 0 and jg >= 8, (lane_split, jg)   # the chunked throughput shape the bench times
+    rng = np.random.default_rng(20)
+    idx = np.unique(np.concatenate([np.linspace(0, n - 1, 128).astype(np.int64), rng.integers(0, n, 128)]))
+    ref = oracle_sample("acc_jerk_kernel", data, idx)
+    e = rel_err("acc_jerk_kernel", [g[idx] for g in got], ref)
+    assert e <= 1e-12, e
+    # Newton's third law at full size: the mass-weighted sums vanish up to rounding
+    m = data["mass"]
+    for g in got:
+        assert abs(np.sum(m * g)) <= 1e-11 * np.sum(np.abs(m * g))
+
+
+@pytest.mark.parametrize("jg", (32, 64))
+def test_forced_many_chunk_plans(jg):
+    """jg = 32 / 64 chunks over blockIdx.y at a size where every chunk is 1-3 tiles, ragged last
+    tile, ni not a multiple of the i-block."""
+    n = 128 * 67 + 19
+    ps = ics.make_plummer(n, seed=3)
+    data = as_dict(ps, "float64")
+    lib = cuda_lib("float64")
+    olib = oracle.load("oracle", "float64")
+    rng = np.random.default_rng(jg)
+    idx = np.sort(rng.choice(n, 192, replace=False))
+    for name in ("acc_jerk_kernel", "acc_kernel", "phi_kernel", "tstep_kernel", "snap_crackle_kernel",
+                 "nreg_Xkernel", "nreg_Vkernel", "pnacc_kernel"):
+        lib.tupan_cuda_force_plan(0, 0, jg)
+        got = cuda_run(name, "float64", data, data)
+        assert last_plan(lib)[2] == jg
+        ref = oracle_sample(name, data, idx)
+        e = rel_err(name, [g[idx] for g in got], ref)
+        assert e <= 1e-12, (name, jg, e)
+        lib.tupan_cuda_force_plan(-1, 0, 1)
+        auto = cuda_run(name, "float64", data, data)
+        assert rel_err(name, got, auto) <= 1e-13, (name, jg)    # same pairs, other summation order
+
+
+def test_rectangular_65536_x_4194304():
+    nj, ni = 1 << 22, 1 << 16
+    ps = ics.make_plummer(nj, seed=2)
+    J = as_dict(ps, "float64")
+    rng = np.random.default_rng(4)
+    pick = np.sort(rng.choice(nj, ni, replace=False))
+    I = {k: np.ascontiguousarray(v[pick]) for k, v in J.items()}
+    got = cuda_run("acc_jerk_kernel", "float64", I, J)
+    sub = np.sort(rng.choice(ni, 64, replace=False))
+    ia = [np.ascontiguousarray(I[a][sub]) for a in S8]
+    ja = [J[a] for a in S8]
+    ref = [np.zeros(len(sub)) for _ in range(6)]
+    oracle.call_threaded(reference_lib(), "acc_jerk_kernel", "float64", CORES, *([len(sub)] + ia + [nj] + ja + ref))
+    e = rel_err("acc_jerk_kernel", [g[sub] for g in got], ref)
+    assert e <= 1e-12, e

@@ -83,11 +83,13 @@ PART2 = {
                               + [ctypes.POINTER(ctypes.c_int)] * 3),
     "tupan_cuda_set_timing": (None, [ctypes.c_int]),
     "tupan_cuda_last_times": (None, [ctypes.POINTER(ctypes.c_float)] * 5),
+    "tupan_cuda_sum_times": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_longlong)]),
     "tupan_cuda_launch_count": (ctypes.c_longlong, []),
     "tupan_cuda_count_launches": (None, [ctypes.c_longlong]),
     "tupan_cuda_sm_count": (ctypes.c_int, []),
     "tupan_cuda_fma_peak": (ctypes.c_int, [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double)]),
+    "tupan_cuda_pipe_probe": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]),
     "tupan_cuda_real_bytes": (ctypes.c_int, []),
     # Part 3: O(N) integrator updates on device-resident state
     "tupan_cuda_step_begin_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -4,7 +4,9 @@
 
 Outputs ``tupan_b200/lib/libtupan_cuda_fp{32,64}.so`` (git-ignored, shipped to the GPU box
 by gpurun).  Objects are cached under ``tupan_b200/lib/obj`` and rebuilt when a source or
-header is newer.
+header is newer; each object's ``ptxas -v`` report is cached next to it and
+``tupan_b200/lib/ptxas.log`` (git-ignored; a copy per round is kept under ``profiles/``) is
+assembled from all of them on every build, cached or not.
 """
 import os
 import subprocess
@@ -36,14 +38,18 @@ def _compile(args):
     unit, tag, hdr_time, verbose = args
     src = os.path.join(SRC, unit + ".cu")
     obj = os.path.join(LIBDIR, "obj", "%s_%s.o" % (unit, tag))
+    log = obj[:-2] + ".ptxas.log"
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
-        return unit, tag, "cached", ""
+        # the ptxas report (registers, spills) of a cached object is kept next to it
+        return unit, tag, "cached", open(log).read() if os.path.exists(log) else ""
     cmd = ([NVCC] + FLAGS + UNIT_FLAGS.get(unit, []) + os.environ.get("TUPAN_NVCC_EXTRA", "").split()
            + (["-DTUPAN_FP64"] if tag == "fp64" else [])
            + ["-c", src, "-o", obj])
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s (%s):\n%s\n%s" % (unit, tag, p.stdout, p.stderr))
+    with open(log, "w") as f:
+        f.write(p.stderr)
     return unit, tag, "built", p.stderr
 
 

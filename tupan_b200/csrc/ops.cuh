@@ -164,6 +164,88 @@ template <typename T> struct AccJerkOp {
 #pragma unroll
         for (int k = 0; k < NO; ++k) out[k][i] = a[k];
     }
+
+    // ---- grouped form (pair_kernel_grouped, fp64): the same 32 FP64 operations per pair, written for
+    // the G = W x U pairs of a row group operation by operation.  Three basic blocks per group:
+    //   1a  differences, then the r2 and r.v chains step by step -- fma(ry, ry, r2) next to
+    //       fma(ry, vy, rv): the second finds ry in the operand-reuse cache;
+    //   1b  x, rsqrt seed + cubic step, 3/x, -alpha, 3 sqrt3 x^-3/2 (no three-register DFMA at all);
+    //   2   v' = v - alpha r for every pair, then per pair g = -(m q3) and the six accumulations,
+    //       all with g as the LAST-defined multiplicand (ptxas puts the operand it shares between
+    //       consecutive DFMAs in one slot when it is the later-defined one).
+    // Measured (profiles/r02_kernel_lab_grouped.txt): 3.2 uncached three-register DFMAs per pair
+    // instead of 9.3, 72.3 instead of 77.2 clocks per pair in the lab kernel.
+#ifndef TUPAN_AJ_GW
+#define TUPAN_AJ_GW 2
+#define TUPAN_AJ_GU 4
+#define TUPAN_AJ_GNT 256
+#endif
+    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT };
+    struct PV { T rx, ry, rz, vx, vy, vz, na, q3, mj; };
+    template <int W, int U>
+    static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int one)
+    {
+        constexpr int G = W * U;
+        T r2[G], rv[G], e[G], y0[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            const T(&si)[NI] = s[p % W];
+            const T(&rw)[NJP] = rows[p / W];
+            o[p].rx = si[IX] - rw[JX]; o[p].ry = si[IY] - rw[JY]; o[p].rz = si[IZ] - rw[JZ];
+            o[p].vx = si[IVX] - rw[J8_VX]; o[p].vy = si[IVY] - rw[J8_VY]; o[p].vz = si[IVZ] - rw[J8_VZ];
+            e[p] = si[IE] + rw[J8_E2];
+            o[p].mj = rw[JM];
+        }
+#pragma unroll 1
+        for (int z = 0; z < one; ++z) {       // block 1a
+#pragma unroll
+            for (int p = 0; p < G; ++p) { r2[p] = o[p].rx * o[p].rx; rv[p] = o[p].rx * o[p].vx; }
+#pragma unroll
+            for (int p = 0; p < G; ++p) { r2[p] = fma(o[p].ry, o[p].ry, r2[p]); rv[p] = fma(o[p].ry, o[p].vy, rv[p]); }
+#pragma unroll
+            for (int p = 0; p < G; ++p) { r2[p] = fma(o[p].rz, o[p].rz, r2[p]); rv[p] = fma(o[p].rz, o[p].vz, rv[p]); }
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x = r2 + e2
+#pragma unroll
+        for (int p = 0; p < G; ++p) y0[p] = rsqrt_seed_masked<false>(e[p], r2[p]);
+        T t[G], h[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = e[p] * y0[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.64951905283832900), T(0.86602540378443865));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1.7320508075688772));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = y0[p] * t[p];                 // sqrt(3/x)
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];                  // 3/x
+#pragma unroll
+        for (int p = 0; p < G; ++p) { o[p].na = -(h[p] * rv[p]); o[p].q3 = h[p] * t[p]; }   // -alpha; 3 sqrt3 x^-3/2
+    }
+    template <int W, int U>
+    static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
+    {
+        constexpr int G = W * U;
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            o[p].vx = fma(o[p].na, o[p].rx, o[p].vx);
+            o[p].vy = fma(o[p].na, o[p].ry, o[p].vy);
+            o[p].vz = fma(o[p].na, o[p].rz, o[p].vz);
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            // the product is formed HERE, after v', on purpose (see above); volatile keeps it in
+            // this block: hoisted out of the one-trip loop it would be defined before v' again
+            T g;
+            asm volatile("mul.f64 %0, %1, %2;" : "=d"(g) : "d"(-o[p].mj), "d"(o[p].q3));
+            T(&ac)[NA] = a[p % W];
+            ac[0] = fma(o[p].rx, g, ac[0]); ac[1] = fma(o[p].ry, g, ac[1]); ac[2] = fma(o[p].rz, g, ac[2]);
+            ac[3] = fma(o[p].vx, g, ac[3]); ac[4] = fma(o[p].vy, g, ac[4]); ac[5] = fma(o[p].vz, g, ac[5]);
+        }
+    }
 };
 
 // =======================================================================================
@@ -231,6 +313,7 @@ template <typename T> struct SnapCrackleOp {
 #pragma unroll
         for (int k = 0; k < NO; ++k) out[k][i] = a[k];
     }
+
 };
 
 // =======================================================================================

@@ -39,6 +39,8 @@
 // idle lanes along each time one lane hits it.  Results return to the owner lane in ring order,
 // which for any given particle is its own j order: the sums stay deterministic.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tupan {
@@ -102,6 +104,7 @@ template <class Op> struct PairArgs {
     T* partial;             // nullptr: apply epilogue and write outputs directly
     OutRefs<T> out;
     typename Op::Params prm;
+    int one;                // always 1; a trip count the compiler cannot see (pair_kernel_grouped)
 };
 
 template <class Op, int TJ, int STAGES> struct PairSmem {
@@ -281,6 +284,132 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
                 } else {
                     Op::finish(a.i.p, i, acc[w], a.prm, a.out.p);
                 }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// pair_kernel_grouped: the throughput shape for Ops that supply their pair body in GROUPED form.
+//
+// What it is for (measured on B200: tools/microbench2.cu, tools/sass_rf.py, tools/kernel_lab2.cu,
+// profiles/r02_microbench_fp64_operands.txt, profiles/r02_kernel_lab_grouped.txt):
+// an FP64 instruction holds the pipe for 2 clocks, but a DFMA whose three sources are three
+// DISTINCT registers needs a THIRD clock to collect its operands, unless the operand-reuse cache
+// serves one of them (the previous instruction of the warp read the same register in the same
+// operand slot).  acc_jerk has 11 such DFMAs among its 32 FP64 instructions per pair (r.v chain,
+// v - alpha r, the six accumulations).  ptxas, scheduling the unrolled loop of pair_kernel as one
+// basic block, interleaves them with everything else and leaves 9 of them uncached: 64 + 9 clocks
+// per pair modelled, 74.4 measured.  Here the G = W x U pairs of a group of U rows are written
+// operation by operation (dependent operations are G instructions apart), and the operand-sharing
+// DFMAs live in basic blocks of their own: a loop whose trip count is a kernel argument (always 1)
+// keeps ptxas from merging the blocks, and inside such a block it groups the DFMAs by shared
+// operand and flags the reuse itself: 3.2 uncached three-register DFMAs per pair instead of 9.
+//
+// An Op opts in with
+//   enum { GROUPED = 1, GW, GU, GNT };   particles per thread, rows per group, threads per CTA
+//   struct PV;                             what phase 1 hands to phase 2 for one pair
+//   group_phase1<W, U>(is, rows, pv, prm, one)   everything up to the accumulation, W x U pairs
+//   group_phase2<W, U>(pv, acc, prm)       the accumulation DFMAs of the group (run inside the
+//                                          kernel's one-trip loop)
+// Partial tiles (the end of a j range) take Op::pair row by row.
+// ---------------------------------------------------------------------------------------
+template <class Op, typename = void> struct Grouped { enum { value = 0, W = 1, U = 1, NT = 256 }; };
+template <class Op> struct Grouped<Op, typename std::enable_if<(Op::GROUPED != 0)>::type> {
+    enum { value = 1, W = Op::GW, U = Op::GU, NT = Op::GNT };
+};
+
+template <class Op, int NT, int W, int U, int TJ, int STAGES, bool MULTI = false>
+__global__ void __launch_bounds__(NT) pair_kernel_grouped(const __grid_constant__ PairArgs<Op> a)
+{
+    typedef typename Op::real T;
+    constexpr int NJP = Packed<Op>::NJP;
+    constexpr int TILE_ELEMS = TJ * NJP;
+    constexpr int G = W * U;
+    static_assert(TJ % U == 0, "a tile holds whole row groups");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tiles = reinterpret_cast<T*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * TILE_ELEMS * sizeof(T));
+
+    const int tid = threadIdx.x;
+    const long long ibase = (long long)blockIdx.x * (NT * W);
+
+    T is[W][Op::NI];
+    T acc[W][Op::NA];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        long long i = ibase + (long long)w * NT + tid;
+        if (i > a.ni - 1) i = a.ni - 1;  // clamp: computes a duplicate, never stored
+        Op::load_i(a.i.p, i, is[w]);
+        Op::zero(acc[w]);
+    }
+
+    const long long jlo = a.j0 + (long long)blockIdx.y * a.jchunk;
+    long long jhi = jlo + a.jchunk;
+    if (jhi > a.j1) jhi = a.j1;
+    const int ntiles = (jhi > jlo) ? (int)((jhi - jlo + TJ - 1) / TJ) : 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {  // elected thread: start the bulk copy of tile t
+        const int s = t % STAGES;
+        int cnt;
+        const T* src = locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
+        const unsigned bytes = (unsigned)cnt * Packed<Op>::ROW_BYTES;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(tiles + s * TILE_ELEMS, src, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < STAGES && t < ntiles; ++t) issue(t);
+    }
+    const int one = a.one;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % STAGES;
+        mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
+        const T* sj = tiles + s * TILE_ELEMS;
+        int cnt;
+        locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
+
+        if (cnt == TJ) {
+#pragma unroll 1
+            for (int j = 0; j < TJ; j += U) {
+                T rows[U][NJP];
+                typename Op::PV pv[G];
+#pragma unroll
+                for (int u = 0; u < U; ++u) load_row<Op>(sj + (j + u) * NJP, rows[u]);
+                Op::template group_phase1<W, U>(is, rows, pv, a.prm, one);
+#pragma unroll 1
+                for (int z = 0; z < one; ++z) Op::template group_phase2<W, U>(pv, acc, a.prm);
+            }
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                T row[NJP];
+                load_row<Op>(sj + j * NJP, row);
+#pragma unroll
+                for (int w = 0; w < W; ++w) Op::pair(is[w], row, acc[w], a.prm);
+            }
+        }
+        __syncthreads();  // every warp is done with stage s -> it may be refilled
+        if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+    }
+
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const long long i = ibase + (long long)w * NT + tid;
+        if (i < a.ni) {
+            if (a.partial != nullptr) {
+                T* dst = a.partial + ((long long)(a.slot0 + blockIdx.y) * Op::NA) * a.ni + i;
+#pragma unroll
+                for (int k = 0; k < Op::NA; ++k) dst[(long long)k * a.ni] = acc[w][k];
+            } else {
+                Op::finish(a.i.p, i, acc[w], a.prm, a.out.p);
             }
         }
     }
@@ -501,6 +630,8 @@ template <class Op, bool LANE_SPLIT> struct KernelOf {
     template <int NT, int TJ, int STAGES, bool MULTI = false> static Fn get()
     {
         if constexpr (Defers<Op>::value != 0) return pair_kernel_defer<Op, NT, TJ, STAGES, LANE_SPLIT, MULTI>;
+        else if constexpr (!LANE_SPLIT && Grouped<Op>::value != 0)
+            return pair_kernel_grouped<Op, NT, Grouped<Op>::W, Grouped<Op>::U, TJ, STAGES, MULTI>;
         else return pair_kernel<Op, NT, LANE_SPLIT ? 1 : Op::WPT, TJ, STAGES, LANE_SPLIT, MULTI>;
     }
 };
@@ -542,7 +673,12 @@ struct DeviceInfo {
 };
 
 template <class Op> struct Tune {
-    enum { NT = 256, TJ = 128, STAGES = 4, NT_SPLIT = 128 };
+    enum {
+        TJ = 128, STAGES = 4, NT_SPLIT = 128,
+        NT = Grouped<Op>::value ? (int)Grouped<Op>::NT : 256,                 // throughput shape
+        WPT = Grouped<Op>::value ? (int)Grouped<Op>::W : (Defers<Op>::value ? 1 : (int)Op::WPT),
+        SMEM = (int)PairSmemDefer<Op, NT, TJ, STAGES>::BYTES
+    };
 };
 
 // Issue cost of one pair on the kernel's main pipe, in warp instructions (FP64 or FP32); the
@@ -583,9 +719,9 @@ inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
     double best = 1e300;
 
     {   // throughput shape
-        const long long IB = (long long)U::NT * Op::WPT;
+        const long long IB = (long long)U::NT * U::WPT;
         const long long iblocks = (ni + IB - 1) / IB;
-        const double tile_us = (double)TJ * Op::WPT * cpw * (U::NT / 32 / 4) / clk_per_us;
+        const double tile_us = (double)TJ * U::WPT * cpw * ((double)U::NT / 32 / 4) / clk_per_us;
         const long long maxg = tiles < 64 ? tiles : 64;
         for (long long g = 1; g <= maxg; ++g) {
             const long long tpc = (tiles + g - 1) / g;            // tiles per chunk
@@ -653,6 +789,7 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
     a.partial = partial;
     a.out = out;
     a.prm = prm;
+    a.one = 1;
     if (ni <= 0) return cudaSuccess;
     int dev_id = 0;
     cudaGetDevice(&dev_id);
@@ -668,9 +805,9 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
     if (!plan.lane_split) {
         auto k = multi ? KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, true>()
                        : KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, false>();
-        const size_t smem = PairSmemDefer<Op, U::NT, U::TJ, U::STAGES>::BYTES;
+        const size_t smem = U::SMEM;
         prepare(k, smem, multi ? 1 : 0);
-        const long long per_cta = (long long)U::NT * Op::WPT;
+        const long long per_cta = (long long)U::NT * U::WPT;
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
         k<<<grid, U::NT, smem, stream>>>(a);
     } else {

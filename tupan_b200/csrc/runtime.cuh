@@ -44,9 +44,14 @@ struct Context {
     HostBuf stage_host;
     // forced launch plan (tests, tuning); lane_split < 0 means "choose"
     Plan forced = {-1, 0, 1};
-    // timing of the last call (only when enabled)
+    // timing (only when enabled): every call records its stage boundaries into its own set of
+    // events, a ring of TIME_RING sets, so that the stage times of all calls since
+    // tupan_cuda_set_timing(1) can be summed afterwards without a host sync in between
+    enum { TIME_RING = 256 };
     bool timing = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t (*evr)[6] = nullptr;
+    unsigned* evmark = nullptr;   // which of a set's events were recorded
+    long long nsets = 0;          // sets started since timing was enabled
     StageTimes last = {0, 0, 0, 0, 0};
     Plan last_plan = {0, 0, 1};
     long long launches = 0;   // kernels launched by this library since load
@@ -55,14 +60,34 @@ struct Context {
 
     int init();
     int fail(cudaError_t e, const char* where);
-    unsigned marked = 0;      // which of ev[] were recorded by the last call
+    int cur_set() const { return (int)((nsets - 1) % TIME_RING); }
+    void begin_set()
+    {
+        nsets++;
+        evmark[cur_set()] = 0;
+    }
     void mark(int k, cudaStream_t s)
     {
-        if (!timing) return;
-        // a new call starts at ev[0] (host-pointer entry) or at ev[1] (device-resident entry)
-        if (k == 0 || (k == 1 && marked != 1u)) marked = 0;
-        cudaEventRecord(ev[k], s);
-        marked |= 1u << k;
+        if (!timing || !evr) return;
+        // a new call starts at event 0 (host-pointer entry), at event 1 (device-resident entry) or
+        // at event 2 (a bare sweep of the multi-GPU path)
+        if (nsets == 0 || k == 0 || (k == 1 && evmark[cur_set()] != 1u) || (k == 2 && !(evmark[cur_set()] & 2u)))
+            begin_set();
+        cudaEventRecord(evr[cur_set()][k], s);
+        evmark[cur_set()] |= 1u << k;
+    }
+    // stage times of set q (stage k lies between events k and k+1); false if nothing was recorded
+    bool set_times(int q, float (&t)[5]) const
+    {
+        bool any = false;
+        for (int k = 0; k < 5; ++k) {
+            t[k] = 0;
+            if ((evmark[q] >> k & 1u) && (evmark[q] >> (k + 1) & 1u) && cudaEventSynchronize(evr[q][k + 1]) == cudaSuccess) {
+                cudaEventElapsedTime(&t[k], evr[q][k], evr[q][k + 1]);
+                any = true;
+            }
+        }
+        return any;
     }
 };
 
@@ -164,8 +189,10 @@ template <class Op> struct Runner {
     {
         Plan p = plan_for(ni, j1 - j0);
         OutRefs<T> none = out_refs(nullptr, 0);
+        ctx().mark(2, s);
         TUPAN_CHECK(launch_pairs<Op>(p, in_refs(di, n_in), ni, packed, j0, j1, prm, partial, slot0, none, s),
                     "pair sweep");
+        ctx().mark(3, s);
         if (ni > 0) ctx().launches++;
         ctx().last_plan = p;
         return 0;
@@ -192,8 +219,10 @@ template <class Op> struct Runner {
         const long long rows = (long long)seg.tile0[seg.nseg] * U::TJ;
         Plan p = plan_for(ni, rows);
         OutRefs<T> none = out_refs(nullptr, 0);
+        c.mark(2, s);
         TUPAN_CHECK(launch_pairs<Op>(p, in_refs(di, n_in), ni, nullptr, 0, rows, prm, partial, slot0, none, s, &seg),
                     "pair sweep (multi-owner)");
+        c.mark(3, s);
         c.launches++;
         c.last_plan = p;
         return 0;
