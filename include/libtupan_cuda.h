@@ -164,12 +164,17 @@ int tupan_cuda_run_dev(int kernel, long long ni, const void *const *iarr, long l
 /* kepler for `pairs` independent binaries: arrays hold 2*pairs bodies, binary b = (2b, 2b+1) */
 int tupan_cuda_kepler_dev(long long pairs, const void *const *arr, double dt, void *const *out, void *stream);
 
-/* The Kepler propagator inside sakura / kepler bounds its sub-step doubling at 2^16 (the
- * reference, universal_kepler_solver.h:481-606, doubles without bound: minutes on a host
- * core for softened tight binaries).  The synchronous Part-1 entry points fail loudly when a
- * pair hits the bound; after asynchronous *_dev calls query it here: returns the number of
- * such pairs since the last query and resets it (synchronises the device); < 0 on error. */
+/* Sub-step doubling of the Kepler propagator (universal_kepler_solver.h:481-606: the reference
+ * doubles without bound, 2^14 .. 2^27 sequential sub-steps for softened tight binaries).  Inside a
+ * sakura sweep a pair gets 2^12 sub-steps; a pair that needs more is handed to a clean-up launch
+ * (one thread per pair, up to 2^30 sub-steps, like the two-body entry point) whose result is added
+ * to the owner's outputs before the call's outputs count as written -- same answer as the
+ * reference, the other pairs do not wait.  Only a pair that exceeds 2^30 is counted here: number of
+ * such pairs since the last query (resets; synchronises the device); < 0 on error.  The
+ * synchronous Part-1 entry points check it themselves and fail loudly. */
 long long tupan_cuda_kepler_limit_hits(void);
+/* pairs handed to the clean-up launch since the library was loaded (synchronises the device) */
+long long tupan_cuda_kepler_cleanup_pairs(void);
 
 /* Building blocks.  A packed j buffer has tupan_cuda_row_width(kernel) REALs per particle
  * (row-major, 16-byte aligned rows) and can be all-gathered across GPUs as one tensor. */

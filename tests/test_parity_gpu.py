@@ -114,15 +114,19 @@ def test_golden_vectors_from_reference(setname, prec):
 def test_kepler_golden_in_place(prec):
     """kepler_solver_kernel: two bodies, outputs alias inputs (extensions.py:642-646).
 
-    Unsoftened binaries must match the reference.  For the softened ones the reference's
-    energy check sub-steps without bound (up to 2^27 sequential steps in these vectors); the
-    CUDA path bounds the doubling at 2^16 sub-steps and must then FAIL LOUDLY, never return
-    an unconverged state silently."""
+    All 18 golden cases of the reference must match, the softened ones included: there the
+    reference's energy check doubles the number of sub-steps without bound (2^14 .. 2^27 SEQUENTIAL
+    sub-steps in these vectors) and so does the two-body entry point (bound 2^30).  The one case
+    that needs 2^27 sub-steps (43 s on a host core, minutes on one GPU thread) only runs with
+    TUPAN_SLOW_TESTS=1; profiles/r02_kepler_softened.txt keeps its result."""
+    import os
     lib = cuda_lib(prec)
     dt_np = np.dtype(prec)
-    tol = tol_for("kepler_solver_kernel", prec)
-    matched = refused = 0
-    for ins, dt, outs in load_kepler(prec):
+    matched = skipped_slow = 0
+    for case, (ins, dt, outs) in enumerate(load_kepler(prec)):
+        if prec == "float64" and case == 10 and not os.environ.get("TUPAN_SLOW_TESTS"):
+            skipped_slow += 1
+            continue
         # The solver removes whole periods from dt (universal_kepler_solver.h:406-412), so an
         # error eps in the period becomes a phase error eps * (number of revolutions): the
         # tolerance is stated per revolution.
@@ -136,20 +140,34 @@ def test_kepler_golden_in_place(prec):
         arrs = [np.ascontiguousarray(ins[a], dt_np).copy() for a in S8]
         res = [arrs[1], arrs[2], arrs[3], arrs[5], arrs[6], arrs[7]]      # in place
         oracle.call(lib, "kepler_solver_kernel", prec, *(arrs + [dt] + res))
-        try:
-            backend.check(lib, "kepler_solver_kernel")
-        except backend.TupanCudaError as err:
-            assert "sub-steps" in str(err)
-            assert float(ins["eps2"][0]) > 0, "only softened orbits may hit the sub-step bound"
-            refused += 1
-            continue
+        backend.check(lib, "kepler_solver_kernel")                       # no case may be refused
         for lo, names in ((0, ("rx", "ry", "rz")), (3, ("vx", "vy", "vz"))):
             g = np.stack(res[lo:lo + 3]).astype(np.float64)
             r = np.stack([outs[k] for k in names]).astype(np.float64)
             e = np.sqrt(((g - r) ** 2).sum(0)) / np.sqrt((r ** 2).sum(0))
-            assert e.max() <= tol, (prec, dt, float(ins["eps2"][0]), e.max())
+            assert e.max() <= tol, (prec, case, dt, float(ins["eps2"][0]), e.max())
         matched += 1
-    assert matched >= (12 if prec == "float64" else 9), (matched, refused)
+    assert matched + skipped_slow == 18 and skipped_slow <= 1, (matched, skipped_slow)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sakura_softened_binaries_take_the_cleanup_launch(prec):
+    """Softened tight binaries: pairs whose Kepler sub-stepping needs more than the sweep's 2^12
+    sub-steps are handed to the clean-up launch and must still come out as the reference's
+    (sakura_kernel_common.h:94-123 -> universal_kepler_solver.h:523-606)."""
+    ps = ics.make_binary_rich(48, relative_size=5.0e-3, seed=3, eps2=5.0e-7)
+    data = as_dict(ps, prec)
+    olib = oracle.load("oracle", prec)
+    lib = cuda_lib(prec)
+    before = lib.tupan_cuda_kepler_cleanup_pairs()
+    floors = state_floors(data)
+    for sc in ((1.0 / 64, 1), (1.0 / 64, -2), (-0.05, 2)):
+        ref = run(olib, "sakura_kernel", prec, data, data, sc)
+        got = cuda_run("sakura_kernel", prec, data, data, sc)
+        e = rel_err("sakura_kernel", got, ref, floors)
+        assert e <= tol_for("sakura_kernel", prec), (prec, sc, e)
+    if prec == "float64":
+        assert lib.tupan_cuda_kepler_cleanup_pairs() > before          # the path was exercised
 
 
 @pytest.mark.parametrize("prec", PRECS)

@@ -14,8 +14,8 @@ using namespace tupan;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
 // the production Op with another group shape; W = 0: the round-1 kernel (not grouped)
-template <int W, int U, int NT_, int UNUSED_> struct AJ : AccJerkOp<double> {
-    enum { GROUPED = W > 0, GW = W > 0 ? W : 1, GU = U, GNT = NT_ };
+template <int W, int U, int NT_, int MODE_> struct AJ : AccJerkOp<double> {
+    enum { GROUPED = W > 0, GW = W > 0 ? W : 1, GU = U, GNT = NT_, GMODE = MODE_ };
 };
 
 template <class Op>
@@ -77,8 +77,8 @@ static double run_variant(const char* name, const InRefs<double>& in, long long 
 #endif
 #ifndef LAB_LIST
 #define LAB_LIST \
-    X(0, 8, 256, 0) X(2, 4, 256, 0) X(3, 2, 256, 0) X(2, 2, 256, 0) X(1, 4, 256, 0) X(1, 8, 256, 0) X(2, 4, 128, 0) \
-    X(1, 4, 512, 0) X(2, 2, 512, 0) X(1, 4, 384, 0) X(2, 2, 384, 0)
+    X(0, 8, 256, 0) X(2, 4, 256, 4) X(2, 4, 256, 7) X(2, 4, 256, 3) X(2, 4, 256, 1) X(2, 4, 256, 0) \
+    X(3, 2, 256, 4) X(3, 2, 256, 5) X(3, 2, 256, 7) X(3, 2, 256, 3)
 #endif
 
 int main(int argc, char** argv)
@@ -108,10 +108,10 @@ int main(int argc, char** argv)
     double* out[6];
     for (int q = 0; q < 6; ++q) CK(cudaMalloc(&out[q], n * sizeof(double)));
     printf("%s, %d SMs, nj = %lld\n", p.name, sms, nj);
-#define X(W, U_, NT_, D) run_variant<AJ<W, U_, NT_, D>>("W" #W " U" #U_ " NT" #NT_, in, n - nj, jpack, nj, out, sms, true);
+#define X(W, U_, NT_, D) run_variant<AJ<W, U_, NT_, D>>("W" #W " U" #U_ " NT" #NT_ " mode" #D, in, n - nj, jpack, nj, out, sms, true);
     LAB_LIST
 #undef X
-#define X(W, U_, NT_, D) run_variant<AJ<W, U_, NT_, D>>("W" #W " U" #U_ " NT" #NT_, in, n - nj, jpack, nj, out, sms, false);
+#define X(W, U_, NT_, D) run_variant<AJ<W, U_, NT_, D>>("W" #W " U" #U_ " NT" #NT_ " mode" #D, in, n - nj, jpack, nj, out, sms, false);
     LAB_LIST
 #undef X
     return 0;

@@ -48,6 +48,7 @@ PART2 = {
     "tupan_cuda_kepler_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_double,
                                              ctypes.c_void_p, ctypes.c_void_p]),
     "tupan_cuda_kepler_limit_hits": (ctypes.c_longlong, []),
+    "tupan_cuda_kepler_cleanup_pairs": (ctypes.c_longlong, []),
     "tupan_cuda_row_width": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "tupan_cuda_n_acc": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "tupan_cuda_pack_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,

@@ -117,6 +117,7 @@ const KernelVTable* vtable(int kernel)
 
 int kepler_run_dev(long long pairs, const real_t* const* din, double dt, real_t* const* dout, cudaStream_t st);
 long long kepler_limit_take();
+long long kepler_cleanup_count();
 
 // ---- |x| minimum (fused tstep follow-up) ------------------------------------------------
 __global__ void abs_min_kernel(const real_t* __restrict__ v, long long n, real_t* __restrict__ out)
@@ -170,11 +171,13 @@ template <int KIND>
 __global__ void __launch_bounds__(256) pipe_probe_kernel(real_t* out, int iters, real_t a)
 {
     real_t x[8], y[8];
+    // y comes from memory so that it lives in registers (a launch constant would be folded into the
+    // instruction as a constant-bank operand: a different operand shape)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { x[k] = (real_t)(threadIdx.x + k); y[k] = a + (real_t)1e-9 * (real_t)k; }
+    for (int k = 0; k < 8; ++k) { x[k] = (real_t)(threadIdx.x + k); y[k] = out[8 + k] * a; }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < 32; ++u) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 if (KIND == 1) x[k] = x[k] + y[k];
@@ -235,6 +238,14 @@ long long tupan_cuda_kepler_limit_hits(void)
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.init()) return -1;
     return kepler_limit_take();
+}
+
+long long tupan_cuda_kepler_cleanup_pairs(void)
+{
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.init()) return -1;
+    return kepler_cleanup_count();
 }
 
 int tupan_cuda_row_width(int kernel, const double* scal)
@@ -449,12 +460,13 @@ int tupan_cuda_pipe_probe(int kind, double ms, double* tera_ops)
     if (kind < 1 || kind > 3) return c.fail(cudaErrorInvalidValue, "pipe_probe: kind 1..3");
     real_t* d = static_cast<real_t*>(c.partial.ensure(256));
     if (!d) return c.fail(cudaErrorMemoryAllocation, "probe buffer");
+    TUPAN_CHECK(cudaMemsetAsync(d, 0, 256, c.stream), "probe buffer");
     cudaEvent_t e0, e1;
     TUPAN_CHECK(cudaEventCreate(&e0), "event");
     TUPAN_CHECK(cudaEventCreate(&e1), "event");
     const int grid = c.info.sm_count * 4, block = 256;
-    const double ops_per_iter = 8.0 * 16 * (double)grid * block;
-    int iters = 2000;
+    const double ops_per_iter = 8.0 * 32 * (double)grid * block;
+    int iters = 1000;
     float t = 0;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0, c.stream);

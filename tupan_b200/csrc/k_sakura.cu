@@ -4,11 +4,22 @@
 
 namespace tupan {
 // scal = dt, flag  (libtupan.h:203-229)
+enum { SAKURA_JOBS_CAP = 1 << 16 };
+static DevBuf g_jobs;        // SAKURA_JOBS_CAP entries + the counter; lives as long as the library
 static inline SakuraParams<real_t> sakura_params(const double* s)
 {
     SakuraParams<real_t> p;
     p.dt = (real_t)s[0];
     p.flag = (int)s[1];
+    // the list of pairs handed to the clean-up launch (kepler.cuh); allocated once, never resized,
+    // so that pointers captured in a CUDA graph stay valid
+    const size_t bytes = (size_t)SAKURA_JOBS_CAP * SAKURA_JOB_REALS * sizeof(real_t);
+    const bool fresh = g_jobs.p == nullptr;
+    char* base = static_cast<char*>(g_jobs.ensure(bytes + 256));
+    if (base && fresh) cudaMemset(base + bytes, 0, 256);
+    p.jobs = reinterpret_cast<real_t*>(base);
+    p.njobs = base ? reinterpret_cast<unsigned*>(base + bytes) : nullptr;
+    p.jobs_cap = base ? (unsigned)SAKURA_JOBS_CAP : 0u;
     return p;
 }
 // one straight-line variant per flag value (as for the PN levels, k_pn.cu)
@@ -43,6 +54,12 @@ long long kepler_limit_take()
     if (hits != 0 && cudaMemcpyToSymbol(kepler_limit_hits, &zero, sizeof(zero)) != cudaSuccess) return -1;
     return (long long)hits;
 }
+long long kepler_cleanup_count()
+{
+    unsigned long long n = 0;
+    if (cudaMemcpyFromSymbol(&n, kepler_cleanup_total, sizeof(n)) != cudaSuccess) return -1;
+    return (long long)n;
+}
 static int kepler_limit_check(const char* where)
 {
     const long long hits = kepler_limit_take();
@@ -51,7 +68,7 @@ static int kepler_limit_check(const char* where)
     c.last_error = hits < 0 ? (int)cudaGetLastError() : -2;
     snprintf(c.last_msg, sizeof(c.last_msg),
              "tupan_cuda: %s: %lld pair(s) needed more than 2^%d Kepler sub-steps (softened tight binary); "
-             "result not converged", where, hits, (int)MAX_DOUBLINGS);
+             "result not converged", where, hits, (int)FULL_DOUBLINGS);
     fprintf(stderr, "%s\n", c.last_msg);
     return c.last_error;
 }

@@ -10,13 +10,20 @@
 // Behaviour that has to match the reference: tolerance 2^-42 (fp64) / 2^-16 (fp32) on the
 // Laguerre step, at most 64 iterations, failure codes trigger a restart with twice as many
 // sub-steps, period reduction for bound orbits, log-based first guess for hyperbolic ones,
-// r2 > 0 mask returns the state unchanged.  One deliberate difference: the two doubling
-// loops are bounded (at most 2^MAX_DOUBLINGS sub-steps) so a pathological pair cannot hang
-// the GPU.  The reference doubles without bound: for SOFTENED tight binaries its energy
-// check (:533-606) drives it to 10^6 .. 10^9 sequential sub-steps (measured with the oracle:
-// eps2 = 1e-8, a ~ 1e-3, dt = 0.37 -> n = 2^30, 6 minutes on a host core).  When the bound is
-// hit the pair is counted in kepler_limit_hits and the host entry points fail loudly
-// (tupan_cuda_last_error) instead of returning an unconverged state silently.
+// r2 > 0 mask returns the state unchanged.
+//
+// Sub-step doubling.  The reference doubles the number of sub-steps without bound, both on a
+// solver failure (:481-520) and in the energy check of softened orbits (:523-606); for SOFTENED
+// tight binaries the latter needs 2^14 .. 2^27 SEQUENTIAL sub-steps in the reference's own golden
+// vectors (tests/golden/kepler_fp64.npz; 43 s on a host core for the worst).  Here the doubling
+// takes a bound as an argument:
+//   * inside the pair sweep (sakura) it is 2^SWEEP_DOUBLINGS, so that one pathological pair cannot
+//     hold 255 other threads of its CTA for minutes; a pair that runs into it is not failed but
+//     handed, with its description, to a clean-up launch (one thread per such pair, see
+//     sakura_cleanup_kernel) whose result is added to the owner's outputs afterwards;
+//   * the clean-up launch and the two-body entry point use 2^FULL_DOUBLINGS = 2^30 sub-steps, i.e.
+//     the reference's behaviour for anything it finishes within hours.  Only beyond that a pair is
+//     counted in kepler_limit_hits and the host entry points fail loudly (tupan_cuda_last_error).
 #pragma once
 #include "ops.cuh"
 
@@ -41,9 +48,10 @@ template <typename T> struct KeplerTol;
 template <> struct KeplerTol<double> { static TUPAN_DEV double value() { return 2.2737367544323205948e-13; } };  // 2^-42
 template <> struct KeplerTol<float>  { static TUPAN_DEV float value() { return 1.52587890625e-5f; } };           // 2^-16
 
-enum { KEPLER_MAXITER = 64, MAX_DOUBLINGS = 16 };
+enum { KEPLER_MAXITER = 64, SWEEP_DOUBLINGS = 12, FULL_DOUBLINGS = 30 };
 
-__device__ unsigned int kepler_limit_hits = 0;   // pairs that ran into MAX_DOUBLINGS (this TU only)
+__device__ unsigned int kepler_limit_hits = 0;   // pairs that ran into FULL_DOUBLINGS (this TU only)
+__device__ unsigned long long kepler_cleanup_total = 0;   // pairs the sweeps handed to the clean-up launch so far
 
 template <typename T> TUPAN_DEV int sgn(T x) { return (x > T(0)) - (x < T(0)); }
 
@@ -161,13 +169,14 @@ template <typename T> TUPAN_DEV int kepler_try(T dt0, T m, T e2, State<T>& p)
     return 0;
 }
 
-// Restart with twice as many equal sub-steps on any failure (:481-520).
-template <typename T> TUPAN_DEV State<T> kepler_substep(T dt, T m, T e2, const State<T>& p0)
+// Restart with twice as many equal sub-steps on any failure (:481-520).  `ok` is cleared when
+// 2^max_doublings sub-steps were not enough.
+template <typename T> TUPAN_DEV State<T> kepler_substep(T dt, T m, T e2, const State<T>& p0, int max_doublings, bool& ok)
 {
     State<T> p = p0;
     int n = 1;
     bool bad = false;
-    for (int level = 0; level <= MAX_DOUBLINGS; ++level) {
+    for (int level = 0; level <= max_doublings; ++level) {
         bad = false;
         p = p0;
         const T h = dt / T(n);
@@ -177,7 +186,7 @@ template <typename T> TUPAN_DEV State<T> kepler_substep(T dt, T m, T e2, const S
         if (!bad) break;
         n *= 2;
     }
-    if (bad) atomicAdd(&kepler_limit_hits, 1u);
+    if (bad) ok = false;
     return p;
 }
 
@@ -189,34 +198,40 @@ template <typename T> TUPAN_DEV T kepler_energy(T m, T e2, const State<T>& p, T&
     return v2 - u;
 }
 
-// Driver with the energy check for softened orbits (:523-614).
-template <typename T> __device__ __noinline__ State<T> kepler_propagate(T dt, T m, T e2, const State<T>& p0)
+// Driver with the energy check for softened orbits (:523-614).  Returns false when the bound on
+// the doubling was hit (the state returned is then meaningless).
+template <typename T>
+__device__ __noinline__ bool kepler_propagate(T dt, T m, T e2, const State<T>& p0, int max_doublings, State<T>& out)
 {
-    State<T> p = kepler_substep(dt, m, e2, p0);
-    if (e2 == T(0)) return p;
+    bool ok = true;
+    State<T> p = kepler_substep(dt, m, e2, p0, max_doublings, ok);
+    out = p;
+    if (!ok) return false;
+    if (e2 == T(0)) return true;
     const T r2 = p0.x * p0.x + p0.y * p0.y + p0.z * p0.z;
-    if (!(r2 > T(0))) return p0;
+    if (!(r2 > T(0))) { out = p0; return true; }
     T u0, u1;
     const T e0 = kepler_energy(m, e2, p0, u0);
     T e1 = kepler_energy(m, e2, p, u1);
     const T tol = T(64) * KeplerTol<T>::value();
-    if (T(2) * k_abs(e1 - e0) < tol * (u1 + u0)) return p;
+    if (T(2) * k_abs(e1 - e0) < tol * (u1 + u0)) return true;
     int n = 1;
     bool bad = true;
-    for (int level = 0; level < MAX_DOUBLINGS; ++level) {
+    for (int level = 0; level < max_doublings; ++level) {
         n *= 2;
         bad = false;
         p = p0;
         const T h = dt / T(n);
         for (int i = 0; i < n; ++i) {
-            p = kepler_substep(h, m, e2, p);
+            p = kepler_substep(h, m, e2, p, max_doublings, ok);
+            if (!ok) return false;
             e1 = kepler_energy(m, e2, p, u1);
             if (T(2) * k_abs(e1 - e0) > tol * (u1 + u0)) { bad = true; break; }
         }
         if (!bad) break;
     }
-    if (bad) atomicAdd(&kepler_limit_hits, 1u);
-    return p;
+    out = p;
+    return !bad;
 }
 
 // Leapfrog (drift-kick-drift) with the softened pair force (sakura_kernel_common.h:45-91).
@@ -238,7 +253,8 @@ template <typename T> TUPAN_DEV void twobody_leapfrog(T dt, T m, T e2, State<T>&
 // test without the division, whose margin covers any rounding of either form --, leaves a masked
 // pair (r2 > 0 false) unchanged as kepler_propagate would, and returns false for everything else; the caller parks such a pair and re-runs it from its initial state with
 // FAST = false, i.e. with the reference's own test.  Parking is always safe.
-template <bool FAST, typename T> TUPAN_DEV bool twobody_step(T dt, T m, T e2, State<T>& p)
+// FAST = false: returns false when the Kepler sub-stepping ran into its bound (2^max_doublings).
+template <bool FAST, typename T> TUPAN_DEV bool twobody_step(T dt, T m, T e2, State<T>& p, int max_doublings = 0)
 {
     const T r2 = p.x * p.x + p.y * p.y + p.z * p.z;
     const T v2 = p.vx * p.vx + p.vy * p.vy + p.vz * p.vz;
@@ -253,29 +269,34 @@ template <bool FAST, typename T> TUPAN_DEV bool twobody_step(T dt, T m, T e2, St
         return !(r2 > T(0));   // masked pair: unchanged, as kepler_propagate would return it
     }
     const T R = T(64) * (m / v2);
-    if (r2 > R * R) twobody_leapfrog(dt, m, e2, p);
-    else p = kepler_propagate(dt, m, e2, p);
-    return true;
+    if (r2 > R * R) {
+        twobody_leapfrog(dt, m, e2, p);
+        return true;
+    }
+    State<T> q;
+    const bool ok = kepler_propagate(dt, m, e2, p, max_doublings, q);
+    p = q;
+    return ok;
 }
 
 // flag in {-2,-1,1,2}: where the free drift is taken out (:126-191); other values: no-op.
-template <bool FAST, typename T> TUPAN_DEV bool twobody_evolve(T dt, int flag, T m, T e2, State<T>& p)
+template <bool FAST, typename T> TUPAN_DEV bool twobody_evolve(T dt, int flag, T m, T e2, State<T>& p, int md = 0)
 {
     if (flag == -1) {
         p.x -= p.vx * dt; p.y -= p.vy * dt; p.z -= p.vz * dt;
-        return twobody_step<FAST>(dt, m, e2, p);
+        return twobody_step<FAST>(dt, m, e2, p, md);
     } else if (flag == 1) {
-        if (!twobody_step<FAST>(dt, m, e2, p)) return false;
+        if (!twobody_step<FAST>(dt, m, e2, p, md)) return false;
         p.x -= p.vx * dt; p.y -= p.vy * dt; p.z -= p.vz * dt;
     } else if (flag == -2) {
         const T h = dt / T(2);
         p.x -= p.vx * h; p.y -= p.vy * h; p.z -= p.vz * h;
-        if (!twobody_step<FAST>(dt, m, e2, p)) return false;
+        if (!twobody_step<FAST>(dt, m, e2, p, md)) return false;
         p.x -= p.vx * h; p.y -= p.vy * h; p.z -= p.vz * h;
     } else if (flag == 2) {
-        if (!twobody_step<FAST>(dt / T(2), m, e2, p)) return false;
+        if (!twobody_step<FAST>(dt / T(2), m, e2, p, md)) return false;
         p.x -= p.vx * dt; p.y -= p.vy * dt; p.z -= p.vz * dt;
-        return twobody_step<FAST>(dt / T(2), m, e2, p);
+        return twobody_step<FAST>(dt / T(2), m, e2, p, md);
     }
     return true;
 }
@@ -283,11 +304,18 @@ template <bool FAST, typename T> TUPAN_DEV bool twobody_evolve(T dt, int flag, T
 // =======================================================================================
 // sakura -- replaces sakura_kernel (sakura_kernel.c:5-64, core sakura_kernel_common.h:194-243)
 // =======================================================================================
-template <typename T> struct SakuraParams { T dt; int flag; };
+// jobs: pairs whose Kepler sub-stepping hit the sweep's bound; each entry is JOB_REALS reals --
+// the pair description d[ND], the owner's particle index (as a real) -- filled by the sweep,
+// replaced by the pair's contribution c[NA] by sakura_cleanup_kernel, applied by sakura_apply_kernel.
+template <typename T> struct SakuraParams { T dt; int flag; T* jobs; unsigned* njobs; unsigned jobs_cap; };
+enum { SAKURA_JOB_REALS = 12 };
 // FLAG is a template parameter: with the flag tested at run time inside the pair, the four
 // variants met at a join point and every pair paid ~40 register moves and 6 branches for it
 // (profiles/r01_sakura_defer_ncu_summary.txt: 139 instructions per pair, 66 of them FP64).
 // FLAG = 0 stands for every other value (no-op, as in the reference).
+template <typename T, int FLAG> __global__ void sakura_cleanup_kernel(SakuraParams<T> p);
+template <typename T> __global__ void sakura_apply_kernel(SakuraParams<T> p, OutRefs<T> out, long long ni);
+
 template <typename T, int FLAG> struct SakuraOp {
     typedef T real;
     typedef SakuraParams<T> Params;
@@ -305,6 +333,7 @@ template <typename T, int FLAG> struct SakuraOp {
     // Deferring sweep (pair_engine.cuh): leapfrog pairs are finished in line, pairs that need
     // the Kepler solver are described by D_* and solved later with full warps.
     enum { D_X, D_Y, D_Z, D_VX, D_VY, D_VZ, D_M, D_E2, D_MJ, ND };
+    static_assert(ND + 1 <= SAKURA_JOB_REALS, "job entry");
     static TUPAN_DEV bool pair_fast(const T (&s)[NI], const T (&row)[NJP], T (&a)[NA], const Params& p, T (&d)[ND])
     {
         State<T> p0;
@@ -325,14 +354,30 @@ template <typename T, int FLAG> struct SakuraOp {
         }
         return true;
     }
-    static TUPAN_DEV void pair_slow(const T (&d)[ND], const Params& p, T (&c)[NA])
+    // false: the sub-stepping hit 2^max_doublings; c is zero and the pair has to be redone
+    static TUPAN_DEV bool pair_slow(const T (&d)[ND], const Params& p, T (&c)[NA], int max_doublings = SWEEP_DOUBLINGS)
     {
         const State<T> p0 = {d[D_X], d[D_Y], d[D_Z], d[D_VX], d[D_VY], d[D_VZ]};
         State<T> q = p0;
-        twobody_evolve<false>(p.dt, FLAG, d[D_M], d[D_E2], q);
-        const T mu = d[D_MJ] / d[D_M];
+        const bool ok = twobody_evolve<false>(p.dt, FLAG, d[D_M], d[D_E2], q, max_doublings);
+        const T mu = ok ? d[D_MJ] / d[D_M] : T(0);
         c[0] = mu * (q.x - p0.x); c[1] = mu * (q.y - p0.y); c[2] = mu * (q.z - p0.z);
         c[3] = mu * (q.vx - p0.vx); c[4] = mu * (q.vy - p0.vy); c[5] = mu * (q.vz - p0.vz);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) c[k] = T(0);
+        }
+        return ok;
+    }
+    // hand a pair the sweep could not finish to the clean-up launch
+    static TUPAN_DEV void defer_to_cleanup(const T (&d)[ND], long long i, const Params& p)
+    {
+        const unsigned k = atomicAdd(p.njobs, 1u);
+        if (k >= p.jobs_cap) { atomicAdd(&kepler_limit_hits, 1u); return; }   // list full: fail loudly
+        T* e = p.jobs + (size_t)k * SAKURA_JOB_REALS;
+#pragma unroll
+        for (int q = 0; q < ND; ++q) e[q] = d[q];
+        e[ND] = (T)i;
     }
     static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA]) { sum_combine(a, b); }
     static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
@@ -340,10 +385,71 @@ template <typename T, int FLAG> struct SakuraOp {
 #pragma unroll
         for (int k = 0; k < NO; ++k) out[k][i] = a[k];
     }
+    // Host side, after the outputs of a call have been written (pair kernel or finalize): finish
+    // the pairs the sweep handed over and add them to the owners' outputs.  Two small launches,
+    // stream-ordered, no host round trip; they find an empty list in the normal case.
+    static cudaError_t after_sweeps(long long ni, const Params& p, const OutRefs<T>& out, cudaStream_t st, long long* launches)
+    {
+        if (FLAG == 0 || ni <= 0 || !p.jobs) return cudaSuccess;
+        sakura_cleanup_kernel<T, FLAG><<<64, 32, 0, st>>>(p);
+        sakura_apply_kernel<T><<<1, 32, 0, st>>>(p, out, ni);
+        if (launches) *launches += 2;
+        return cudaGetLastError();
+    }
 };
 
 template <typename T, int FLAG> struct Defers<SakuraOp<T, FLAG>> { enum { value = 1 }; };
 template <typename T, int FLAG> struct OpCost<SakuraOp<T, FLAG>> { enum { value = (FLAG == 2 || FLAG == -2) ? 90 : 62 }; };
+
+// The pairs the sweep handed over: one thread each, the reference's unbounded sub-stepping
+// (2^FULL_DOUBLINGS).  The entry's description is replaced by the pair's contribution.
+template <typename T, int FLAG>
+__global__ void sakura_cleanup_kernel(SakuraParams<T> p)
+{
+    typedef SakuraOp<T, FLAG> Op;
+    unsigned n = *p.njobs;
+    if (n > p.jobs_cap) n = p.jobs_cap;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        T* e = p.jobs + (size_t)k * SAKURA_JOB_REALS;
+        T d[Op::ND], c[Op::NA];
+#pragma unroll
+        for (int q = 0; q < Op::ND; ++q) d[q] = e[q];
+        if (!Op::pair_slow(d, p, c, FULL_DOUBLINGS)) atomicAdd(&kepler_limit_hits, 1u);
+#pragma unroll
+        for (int q = 0; q < Op::NA; ++q) e[q] = c[q];
+    }
+}
+// Add the contributions to the owners' outputs in a fixed order (by owner, then by value), so that
+// the result does not depend on the order in which the sweep appended them; resets the list.
+template <typename T>
+__global__ void sakura_apply_kernel(SakuraParams<T> p, OutRefs<T> out, long long ni)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned n = *p.njobs;
+    if (n > p.jobs_cap) n = p.jobs_cap;
+    enum { OWNER = 9 };                       // SakuraOp::ND
+    for (unsigned done = 0; done < n; ++done) {
+        // selection: the smallest (owner, first component) not applied yet; applied entries get owner -1
+        int best = -1;
+        for (unsigned k = 0; k < n; ++k) {
+            const T* e = p.jobs + (size_t)k * SAKURA_JOB_REALS;
+            if (e[OWNER] < T(0)) continue;
+            if (best < 0) { best = (int)k; continue; }
+            const T* b = p.jobs + (size_t)best * SAKURA_JOB_REALS;
+            if (e[OWNER] < b[OWNER] || (e[OWNER] == b[OWNER] && e[0] < b[0])) best = (int)k;
+        }
+        if (best < 0) break;
+        T* e = p.jobs + (size_t)best * SAKURA_JOB_REALS;
+        const long long i = (long long)e[OWNER];
+        if (i >= 0 && i < ni) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) out.p[q][i] += e[q];
+        }
+        e[OWNER] = T(-1);
+    }
+    kepler_cleanup_total += n;
+    *p.njobs = 0u;
+}
 
 // =======================================================================================
 // Two-body Kepler kernel -- replaces kepler_solver_kernel (kepler_solver_kernel.c:5-50).
@@ -369,7 +475,8 @@ __global__ void kepler_pairs_kernel(InRefs<T> in, long long pairs, T dt, OutRefs
     T cx = imu * x0 + jmu * x1, cy = imu * y0 + jmu * y1, cz = imu * z0 + jmu * z1;
     const T cu = imu * u0 + jmu * u1, cv = imu * v0 + jmu * v1, cw = imu * w0 + jmu * w1;
     cx += cu * dt; cy += cv * dt; cz += cw * dt;
-    const State<T> q = kepler_propagate(dt, m, e2, rel);
+    State<T> q;
+    if (!kepler_propagate(dt, m, e2, rel, FULL_DOUBLINGS, q)) atomicAdd(&kepler_limit_hits, 1u);
     out.p[0][i0] = cx + jmu * q.x;  out.p[1][i0] = cy + jmu * q.y;  out.p[2][i0] = cz + jmu * q.z;
     out.p[3][i0] = cu + jmu * q.vx; out.p[4][i0] = cv + jmu * q.vy; out.p[5][i0] = cw + jmu * q.vz;
     out.p[0][i1] = cx - imu * q.x;  out.p[1][i1] = cy - imu * q.y;  out.p[2][i1] = cz - imu * q.z;

@@ -180,9 +180,10 @@ template <typename T> struct AccJerkOp {
 #define TUPAN_AJ_GU 4
 #define TUPAN_AJ_GNT 256
 #endif
-    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT };
+    // GMODE bit 0: block 1a on its own; bit 1: g formed in block 2 (see above)
+    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT, GMODE = 3 };
     struct PV { T rx, ry, rz, vx, vy, vz, na, q3, mj; };
-    template <int W, int U>
+    template <int W, int U, int MODE>
     static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int one)
     {
         constexpr int G = W * U;
@@ -197,7 +198,7 @@ template <typename T> struct AccJerkOp {
             o[p].mj = rw[JM];
         }
 #pragma unroll 1
-        for (int z = 0; z < one; ++z) {       // block 1a
+        for (int z = 0; z < ((MODE & 1) ? one : 1); ++z) {       // block 1a
 #pragma unroll
             for (int p = 0; p < G; ++p) { r2[p] = o[p].rx * o[p].rx; rv[p] = o[p].rx * o[p].vx; }
 #pragma unroll
@@ -224,11 +225,29 @@ template <typename T> struct AccJerkOp {
         for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];                  // 3/x
 #pragma unroll
         for (int p = 0; p < G; ++p) { o[p].na = -(h[p] * rv[p]); o[p].q3 = h[p] * t[p]; }   // -alpha; 3 sqrt3 x^-3/2
+        if (!(MODE & 2)) {
+#pragma unroll
+            for (int p = 0; p < G; ++p) o[p].q3 = -(o[p].mj * o[p].q3);      // g
+        }
     }
-    template <int W, int U>
+    template <int W, int U, int MODE>
     static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
     {
         constexpr int G = W * U;
+        if (MODE & 4) {          // pair by pair
+#pragma unroll
+            for (int p = 0; p < G; ++p) {
+                o[p].vx = fma(o[p].na, o[p].rx, o[p].vx);
+                o[p].vy = fma(o[p].na, o[p].ry, o[p].vy);
+                o[p].vz = fma(o[p].na, o[p].rz, o[p].vz);
+                T g = o[p].q3;
+                if (MODE & 2) asm volatile("mul.f64 %0, %1, %2;" : "=d"(g) : "d"(-o[p].mj), "d"(o[p].q3));
+                T(&ac)[NA] = a[p % W];
+                ac[0] = fma(g, o[p].rx, ac[0]); ac[1] = fma(g, o[p].ry, ac[1]); ac[2] = fma(g, o[p].rz, ac[2]);
+                ac[3] = fma(g, o[p].vx, ac[3]); ac[4] = fma(g, o[p].vy, ac[4]); ac[5] = fma(g, o[p].vz, ac[5]);
+            }
+            return;
+        }
 #pragma unroll
         for (int p = 0; p < G; ++p) {
             o[p].vx = fma(o[p].na, o[p].rx, o[p].vx);
@@ -239,8 +258,8 @@ template <typename T> struct AccJerkOp {
         for (int p = 0; p < G; ++p) {
             // the product is formed HERE, after v', on purpose (see above); volatile keeps it in
             // this block: hoisted out of the one-trip loop it would be defined before v' again
-            T g;
-            asm volatile("mul.f64 %0, %1, %2;" : "=d"(g) : "d"(-o[p].mj), "d"(o[p].q3));
+            T g = o[p].q3;
+            if (MODE & 2) asm volatile("mul.f64 %0, %1, %2;" : "=d"(g) : "d"(-o[p].mj), "d"(o[p].q3));
             T(&ac)[NA] = a[p % W];
             ac[0] = fma(o[p].rx, g, ac[0]); ac[1] = fma(o[p].ry, g, ac[1]); ac[2] = fma(o[p].rz, g, ac[2]);
             ac[3] = fma(o[p].vx, g, ac[3]); ac[4] = fma(o[p].vy, g, ac[4]); ac[5] = fma(o[p].vz, g, ac[5]);

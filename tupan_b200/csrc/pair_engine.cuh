@@ -33,7 +33,9 @@
 //   enum { ND };                                    reals that describe one deferred pair
 //   bool pair_fast(s, row, a, prm, real (&d)[ND])   cheap case: accumulate, return false;
 //                                                   expensive case: fill d, return true
-//   pair_slow(d, prm, real (&c)[NA])                full evaluation of one deferred pair
+//   bool pair_slow(d, prm, real (&c)[NA])           full evaluation of one deferred pair; false if
+//                                                   even that gave up (bounded sub-stepping): c = 0
+//   defer_to_cleanup(d, i, prm)                     ... and the pair is handed to a later launch
 // pair_kernel_defer parks the expensive pairs of a warp in a shared-memory ring and runs them
 // 32 at a time, one per lane, so the slow path executes with full warps instead of dragging 31
 // idle lanes along each time one lane hits it.  Results return to the owner lane in ring order,
@@ -370,34 +372,54 @@ __global__ void __launch_bounds__(NT) pair_kernel_grouped(const __grid_constant_
     }
     const int one = a.one;
 
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t % STAGES;
-        mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
-        const T* sj = tiles + s * TILE_ELEMS;
-        int cnt;
-        locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
-
-        if (cnt == TJ) {
+    auto grouped_tile = [&](const T* sj) {
 #pragma unroll 1
-            for (int j = 0; j < TJ; j += U) {
-                T rows[U][NJP];
-                typename Op::PV pv[G];
+        for (int j = 0; j < TJ; j += U) {
+            T rows[U][NJP];
+            typename Op::PV pv[G];
 #pragma unroll
-                for (int u = 0; u < U; ++u) load_row<Op>(sj + (j + u) * NJP, rows[u]);
-                Op::template group_phase1<W, U>(is, rows, pv, a.prm, one);
+            for (int u = 0; u < U; ++u) load_row<Op>(sj + (j + u) * NJP, rows[u]);
+            Op::template group_phase1<W, U, Op::GMODE>(is, rows, pv, a.prm, one);
 #pragma unroll 1
-                for (int z = 0; z < one; ++z) Op::template group_phase2<W, U>(pv, acc, a.prm);
-            }
-        } else {
-            for (int j = 0; j < cnt; ++j) {
-                T row[NJP];
-                load_row<Op>(sj + j * NJP, row);
-#pragma unroll
-                for (int w = 0; w < W; ++w) Op::pair(is[w], row, acc[w], a.prm);
-            }
+            for (int z = 0; z < one; ++z) Op::template group_phase2<W, U, Op::GMODE>(pv, acc, a.prm);
         }
-        __syncthreads();  // every warp is done with stage s -> it may be refilled
-        if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+    };
+    auto plain_tile = [&](const T* sj, int cnt) {
+        for (int j = 0; j < cnt; ++j) {
+            T row[NJP];
+            load_row<Op>(sj + j * NJP, row);
+#pragma unroll
+            for (int w = 0; w < W; ++w) Op::pair(is[w], row, acc[w], a.prm);
+        }
+    };
+
+    if (!MULTI) {
+        // one buffer: every tile but possibly the last is full -- the hot loop has no case split
+        const int nfull = (int)((jhi - jlo) / TJ);
+        for (int t = 0; t < nfull; ++t) {
+            const int s = t % STAGES;
+            mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
+            grouped_tile(tiles + s * TILE_ELEMS);
+            __syncthreads();  // every warp is done with stage s -> it may be refilled
+            if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+        }
+        if (nfull < ntiles) {
+            const int s = nfull % STAGES;
+            mbar_wait(&full[s], (unsigned)(nfull / STAGES) & 1u);
+            plain_tile(tiles + s * TILE_ELEMS, (int)((jhi - jlo) - (long long)nfull * TJ));
+        }
+    } else {
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % STAGES;
+            mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
+            const T* sj = tiles + s * TILE_ELEMS;
+            int cnt;
+            locate_tile<Op, TJ, MULTI>(a, jlo + (long long)t * TJ, jhi, cnt);
+            if (cnt == TJ) grouped_tile(sj);
+            else plain_tile(sj, cnt);
+            __syncthreads();
+            if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+        }
     }
 
 #pragma unroll
@@ -483,13 +505,16 @@ __device__ __noinline__ int sweep_rows(SweepState<Op>* st, const typename Op::re
 // nvcc 12.9 produced wrong results for softened pairs (bisected on a B200 against the golden
 // vectors); the hot loop is unaffected either way, it lives in sweep_rows.
 template <class Op>
-__device__ __forceinline__ void deferred_pair(typename Op::real* slot, typename Op::Params prm)
+__device__ __forceinline__ void deferred_pair(typename Op::real* slot, typename Op::Params prm, long long owner,
+                                              long long ni)
 {
     typedef typename Op::real T;
     T d[Op::ND], c[Op::NA];
 #pragma unroll
     for (int k = 0; k < Op::ND; ++k) d[k] = slot[k];
-    Op::pair_slow(d, prm, c);
+    // a pair the bounded solver gave up on contributes 0 here and goes to the clean-up launch
+    // (not for the clamped duplicates beyond ni: they are never stored)
+    if (!Op::pair_slow(d, prm, c) && owner < ni) Op::defer_to_cleanup(d, owner, prm);
 #pragma unroll
     for (int k = 0; k < Op::NA; ++k) slot[k] = c[k];
 }
@@ -564,7 +589,12 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
     auto drain = [&](int n) {
         __syncwarp();
         const int qhead = st.qhead;
-        if (lane < n) deferred_pair<Op>(qdat + ((qhead + lane) & (QCAP - 1)) * ND, a.prm);
+        if (lane < n) {
+            const int slot = (qhead + lane) & (QCAP - 1);
+            const int ol = qown[slot];                       // the lane that owns this pair
+            const long long owner = ibase + (tid >> 5) * ipw + (ol & (ipw - 1));
+            deferred_pair<Op>(qdat + slot * ND, a.prm, owner, a.ni);
+        }
         __syncwarp();
         for (int e = 0; e < n; ++e) {
             const int slot = (qhead + e) & (QCAP - 1);

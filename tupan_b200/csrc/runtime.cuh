@@ -233,6 +233,14 @@ template <class Op> struct Runner {
         TUPAN_CHECK(launch_finalize<Op>(in_refs(di, n_in), ni, partial, nslots, out_refs(dout, n_out), prm, s),
                     "finalize");
         if (ni > 0) ctx().launches++;
+        return after_outputs(n_out, ni, prm, dout, s);
+    }
+    // Ops with a deferred slow case (sakura) may have handed pairs to a clean-up launch
+    static int after_outputs(int n_out, long long ni, const typename Op::Params& prm, T* const* dout, cudaStream_t s)
+    {
+        if constexpr (Defers<Op>::value != 0) {
+            TUPAN_CHECK(Op::after_sweeps(ni, prm, out_refs(dout, n_out), s, &ctx().launches), "clean-up of deferred pairs");
+        }
         return 0;
     }
 
@@ -256,6 +264,8 @@ template <class Op> struct Runner {
                         "pair kernel");
             c.launches++;
             c.mark(3, s);
+            rc = after_outputs(n_out, ni, prm, dout, s);
+            if (rc) return rc;
         } else {
             T* part = static_cast<T*>(c.partial.ensure((size_t)p.jg * Op::NA * ni * sizeof(T)));
             if (!part) return c.fail(cudaErrorMemoryAllocation, "partial workspace");
