@@ -307,6 +307,11 @@ int tupan_cuda_block_predict_dev(int order, long long n, const void *const *stat
 int tupan_cuda_block_correct_dev(int order, long long n, const void *tau, const void *const *rv0,
                                  const void *const *d0, const void *const *d1, void *const *rv,
                                  void *stream);
+/* block_select: the next block time t = min_i (time[i] + dt[i]) and the ascending list of the
+ * particles that reach it, one launch: d_out2[0] = t, d_out2[1] = their number (two doubles),
+ * d_idx = their indices (n int64 slots). */
+int tupan_cuda_block_select_dev(long long n, const void *time, const void *dt, void *d_out2, void *d_idx,
+                                void *stream);
 /* block_quantize: new step of the n particles that arrived at t_next -- the largest power of two
  * <= ts[i] (tupan's pairwise criterion, tstep_kernel), <= dt_max, <= 2 tau[i] and commensurate
  * with t_next -- and their new time stamp. */

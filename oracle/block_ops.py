@@ -33,14 +33,37 @@ class OracleOps(object):
     def download(self, a):
         return np.array(a)
 
-    def next_time(self, time, dt):
-        return float((time + dt).min())
-
-    def active(self, time, dt, t_next):
-        return np.nonzero((time + dt) == t_next)[0]
+    def select(self, time, dt):
+        t_next = float((time + dt).min())
+        return t_next, np.nonzero((time + dt) == t_next)[0]
 
     def count(self, idx):
         return int(len(idx))
+
+    def part(self, idx, lo, hi):
+        return idx[lo:hi]
+
+    def gather(self, buf, world, group=None):
+        """[rows, chunk] of every rank -> [rows, world * chunk]; gloo in the CPU tests."""
+        if world == 1:
+            return buf
+        import torch
+        import torch.distributed as dist
+        rows, chunk = buf.shape
+        out = torch.empty(world * rows * chunk, dtype=torch.float64)
+        dist.all_gather_into_tensor(out, torch.from_numpy(np.ascontiguousarray(buf)).reshape(-1), group=group)
+        return out.view(world, rows, chunk).permute(1, 0, 2).reshape(rows, world * chunk).numpy().copy()
+
+    def pad(self, block, chunk):
+        rows, k = block.shape
+        if k == chunk:
+            return block
+        out = np.zeros((rows, chunk))
+        out[:, :k] = block
+        return out
+
+    def cat(self, blocks):
+        return np.concatenate(blocks, 0)
 
     def take(self, block, idx):
         return np.ascontiguousarray(block[:, idx])

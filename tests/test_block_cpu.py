@@ -74,3 +74,65 @@ def test_step_quantisation_rules():
     o.quantize(ts, tau, 0.375, 0.25, dt, tm)         # 0.375 is NOT a multiple of 0.25: no doubling of 1/8
     assert np.array_equal(dt[:5], [0.125, 0.125, 0.125, 2.0 ** -10, 0.125])
     assert np.array_equal(dt[5:], [0.0625, 0.0625])  # 0.375 is a multiple of 1/16
+
+
+# ---- the i-sharded block step (BASELINE.json configs[2]) with gloo, world sizes 2 and 3 ----------
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _sharded_worker(rank, world, port, order, n, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = BlockHermite(1.0 / 32, ics.make_plummer(n, seed=5), order=order, dt_max=2.0 ** -4, ops=OracleOps())
+        assert b.world == world and b.rank == rank
+        b.evolve(0.125)
+        out = b.download(ics.make_plummer(n, seed=5))
+        q.put((rank, b.block_steps, b.particle_steps, b.pairs,
+               {k: np.array(getattr(out, k)) for k in ("rx", "ry", "rz", "vx", "vy", "vz", "time", "tstep")}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,order", ((2, 4), (3, 6)))
+def test_sharded_block_steps_equal_the_single_process_run(world, order):
+    """Replicated state, sharded active set: every rank must end with the same state as one
+    process on its own (same kernels on the same pairs; only the batching of the i-set differs,
+    and the oracle's j loop is sequential, so the result is bit-identical), and the pair
+    interactions must be shared out between the ranks."""
+    import torch.multiprocessing as mp
+    n = 61                                         # not a multiple of the world size
+    ref = BlockHermite(1.0 / 32, ics.make_plummer(n, seed=5), order=order, dt_max=2.0 ** -4, ops=OracleOps())
+    ref.evolve(0.125)
+    want = ref.download(ics.make_plummer(n, seed=5))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, order, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        got = [q.get(timeout=120) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(30)
+            if p.is_alive():
+                p.terminate()
+    assert all(p.exitcode == 0 for p in procs)
+    pairs = 0.0
+    for rank, bsteps, psteps, prs, state in got:
+        assert bsteps == ref.block_steps and psteps == ref.particle_steps
+        for k, v in state.items():
+            assert np.array_equal(v, getattr(want, k)), (rank, k)
+        pairs += prs
+        assert prs < 0.75 * ref.pairs              # no rank did (nearly) all the work
+    assert pairs == ref.pairs

@@ -99,6 +99,8 @@ PART2 = {
     "tupan_cuda_block_correct_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p]),
+    "tupan_cuda_block_select_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p]),
     "tupan_cuda_block_quantize_dev": (ctypes.c_int, [ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
                                                      ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
                                                      ctypes.c_void_p, ctypes.c_void_p]),

@@ -7,10 +7,13 @@ namespace tupan {
 void* DevBuf::ensure(size_t bytes)
 {
     if (bytes <= cap && p) return p;
-    if (p) cudaFree(p);
+    // The old block is RETIRED, not freed: a CUDA graph captured by a caller (Integrator steps) has
+    // its address baked in and must keep replaying against valid memory; blocks grow geometrically,
+    // so what is retired stays below the size of the live block.
+    if (p) retired.push_back(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    size_t want = bytes + bytes / 2 + 256;
     if (cudaMalloc(&p, want) != cudaSuccess) {
         p = nullptr;
         return nullptr;
@@ -21,6 +24,8 @@ void* DevBuf::ensure(size_t bytes)
 void DevBuf::release()
 {
     if (p) cudaFree(p);
+    for (void* q : retired) cudaFree(q);
+    retired.clear();
     p = nullptr;
     cap = 0;
 }

@@ -251,6 +251,62 @@ __global__ void __launch_bounds__(256) block_correct_kernel(const BlockCorrectRe
 // New step of the particles that just arrived at block time t_next: the largest power of two
 // not above the criterion ts, at most dt_max, at most twice the old step tau -- and twice only if
 // t_next is a multiple of it (block steps stay commensurate).  Also stamps their new time.
+// block_select: next block time t = min_i(time_i + dt_i) and the ordered list of the particles
+// that reach it, in ONE launch of one CTA (N is a few 10^5: two passes over 2 arrays), so that a
+// block step reads back 16 bytes once instead of synchronising for a minimum, a nonzero() and a
+// count.  out2[0] = t, out2[1] = number of active particles; idx = their indices, ascending.
+__global__ void __launch_bounds__(1024) block_select_kernel(long long n, const real_t* __restrict__ time,
+                                                            const real_t* __restrict__ dt, double* __restrict__ out2,
+                                                            long long* __restrict__ idx)
+{
+    __shared__ double smin[32];
+    __shared__ int scount[32];
+    __shared__ long long sbase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double m = INFINITY;
+    for (long long i = tid; i < n; i += 1024) {
+        const double t = (double)(time[i] + dt[i]);
+        m = t < m ? t : m;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = o < m ? o : m;
+    }
+    if (lane == 0) smin[warp] = m;
+    __syncthreads();
+    m = smin[lane];
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = o < m ? o : m;
+    }
+    const real_t tn = (real_t)m;          // every thread holds the minimum
+    if (tid == 0) sbase = 0;
+    __syncthreads();
+    // ordered compaction, 1024 particles per round
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + tid;
+        const bool act = i < n && (time[i] + dt[i]) == tn;
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) scount[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int c = scount[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        const long long b0 = sbase;
+        if (act) idx[b0 + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (tid == 0) sbase = b0 + total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out2[0] = m;
+        out2[1] = (double)sbase;
+    }
+}
+
 __global__ void __launch_bounds__(256) block_quantize_kernel(long long n, const real_t* __restrict__ ts,
                                                              const real_t* __restrict__ tau, double t_next,
                                                              double dt_max, real_t* __restrict__ dt_new,
@@ -467,8 +523,10 @@ __global__ void __launch_bounds__(256) reduce_stage2_kernel(int what, const doub
         if (what == RED_HALF_DOT) v = 0.5 * v;
         if (what == RED_SAKURA_DT) {
             // dt_sakura = eta / (1 + max)^0.5 in REAL (sakura.py:109-110)
+            // (a shard without particles reduces to the identity -inf: it must not turn the
+            // all-reduced minimum of the ranks into NaN -> dt = eta, which never wins the minimum)
             const real_t eta = (real_t)param;
-            v = (double)(eta / sqrt((real_t)1 + (real_t)v));
+            v = nparts > 0 && v > -(double)INFINITY ? (double)(eta / sqrt((real_t)1 + (real_t)v)) : (double)eta;
         }
         *out = v;
     }
@@ -609,6 +667,20 @@ int tupan_cuda_block_correct_dev(int order, long long n, const void* tau, const 
     if (nd == 2) block_correct_kernel<2><<<blocks_for(n), 256, 0, s>>>(a);
     else block_correct_kernel<3><<<blocks_for(n), 256, 0, s>>>(a);
     TUPAN_CHECK(cudaGetLastError(), "block_correct_kernel");
+    c->launches++;
+    return 0;
+}
+
+int tupan_cuda_block_select_dev(long long n, const void* time, const void* dt, void* d_out2, void* d_idx, void* stream)
+{
+    Context* c;
+    std::lock_guard<std::mutex> lock(ctx().mu);
+    int rc = begin_call(c);
+    if (rc) return rc;
+    if (n <= 0) return c->fail(cudaErrorInvalidValue, "block_select: no particles");
+    block_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, (const real_t*)time, (const real_t*)dt,
+                                                              (double*)d_out2, (long long*)d_idx);
+    TUPAN_CHECK(cudaGetLastError(), "block_select_kernel");
     c->launches++;
     return 0;
 }

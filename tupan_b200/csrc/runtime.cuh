@@ -5,6 +5,7 @@
 #include <mutex>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 #include "pair_engine.cuh"
 
@@ -18,6 +19,7 @@ enum KernelId {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    std::vector<void*> retired;   // outgrown blocks, kept alive (see ensure)
     void* ensure(size_t bytes);
     void release();
 };
@@ -57,6 +59,35 @@ struct Context {
     long long launches = 0;   // kernels launched by this library since load
     int last_error = 0;       // 0 = ok, else cudaError_t (or -1 for argument errors)
     char last_msg[256] = {0};
+
+    // The packed-row and accumulator scratch (jpack, partial) is shared by every call of the process,
+    // whatever stream the caller passes: a call on another stream than the previous one first waits
+    // for the event the previous call recorded behind its last use of the scratch.  (Skipped while a
+    // stream is being captured into a CUDA graph: the graph's own launches are ordered by the capture.)
+    cudaEvent_t scratch_done = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
+    static bool capturing(cudaStream_t s)
+    {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        return cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+    }
+    void scratch_acquire(cudaStream_t s)
+    {
+        if (capturing(s)) return;
+        if (scratch_used && scratch_stream != s && scratch_done) cudaStreamWaitEvent(s, scratch_done, 0);
+    }
+    void scratch_release(cudaStream_t s)
+    {
+        if (capturing(s)) return;
+        if (!scratch_done && cudaEventCreateWithFlags(&scratch_done, cudaEventDisableTiming) != cudaSuccess) {
+            scratch_done = nullptr;
+            return;
+        }
+        cudaEventRecord(scratch_done, s);
+        scratch_stream = s;
+        scratch_used = true;
+    }
 
     int init();
     int fail(cudaError_t e, const char* where);
@@ -252,6 +283,7 @@ template <class Op> struct Runner {
         if (ni <= 0) return 0;
         T* packed = static_cast<T*>(c.jpack.ensure((size_t)(nj > 0 ? nj : 1) * NJP * sizeof(T)));
         if (!packed) return c.fail(cudaErrorMemoryAllocation, "packed j buffer");
+        c.scratch_acquire(s);
         c.mark(1, s);
         int rc = pack(n_in, nj, dj, packed, s);
         if (rc) return rc;
@@ -278,6 +310,7 @@ template <class Op> struct Runner {
             if (rc) return rc;
         }
         c.mark(4, s);
+        c.scratch_release(s);
         return 0;
     }
 

@@ -128,6 +128,8 @@ class _Lib(object):
         self.lib = backend.require_gpu(prec)
         self._ptrs = {}
 
+    PTR_CACHE_MAX = 4096
+
     def ptrs(self, tensors):
         key = tuple(t.data_ptr() for t in tensors)
         p = self._ptrs.get(key)
@@ -135,8 +137,24 @@ class _Lib(object):
             for t in tensors:
                 if not (t.is_cuda and t.is_contiguous()):
                     raise TypeError("contiguous CUDA tensors required")
+            if len(self._ptrs) >= self.PTR_CACHE_MAX:
+                # the hierarchical SIA recursion makes fresh sub-system tensors every step: the cache
+                # only pays for the long-lived state arrays, so it is simply dropped when it fills up
+                self._ptrs.clear()
             p = self._ptrs[key] = (ctypes.c_void_p * len(key))(*key)
         return p
+
+    def check_async(self):
+        """Failures of asynchronous device work that only leave a counter behind: a peer barrier of
+        the p2p transport that gave up waiting, a Kepler pair beyond 2^30 sub-steps.  Called where
+        the integrators synchronise anyway (clock read-back, state download)."""
+        hits = self.lib.tupan_cuda_peer_timeouts()
+        if hits:
+            raise backend.TupanCudaError("peer barrier: %d wait(s) timed out -- forces of this run are not "
+                                         "trustworthy" % hits)
+        hits = self.lib.tupan_cuda_kepler_limit_hits()
+        if hits:
+            raise backend.TupanCudaError("%d Kepler pair(s) needed more than 2^30 sub-steps" % hits)
 
     @staticmethod
     def stream():
@@ -359,6 +377,7 @@ class Integrator(object):
             for _ in range(check_every):
                 self.evolve_step(t_end)
             c = self.ctl.cpu()
+            self.L.check_async()               # a sync point anyway: surface asynchronous failures here
             if not (abs(float(c[CTL_T_CURR])) < abs(t_end)):
                 break
             if max_steps is not None and int(c[CTL_NSTEPS]) >= max_steps:
@@ -376,6 +395,7 @@ class Integrator(object):
     @property
     def particle_system(self):
         self.st.download(self.ps)
+        self.L.check_async()
         return self.ps
 
     def energies(self):

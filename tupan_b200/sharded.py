@@ -301,7 +301,22 @@ class ShardedKernel(object):
         peer.barrier()                               # everybody is done reading: rows may be repacked
         if ni > 0:
             eng.finalize(self.kernel, it, self._partial, slot, scalars, ot)
+        # A barrier that gave up waiting leaves only a counter behind (the sweep went on over stale
+        # rows).  Checking it costs a device synchronisation, so it is done every CHECK_EVERY
+        # evaluations here and at every synchronisation point of the integrators
+        # (integrator._Lib.check_async); `check()` forces it.
+        self._since_check = getattr(self, "_since_check", 0) + 1
+        if self._since_check >= self.CHECK_EVERY:
+            self.check()
         return out
+
+    CHECK_EVERY = 64
+
+    def check(self):
+        """Synchronise and raise if a peer barrier of this process timed out."""
+        self._since_check = 0
+        if self.peer is not None:
+            self.peer.check()
 
     def evaluate(self, local, scalars=(), out=None):
         if self.transport == "p2p":
