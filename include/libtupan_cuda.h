@@ -167,9 +167,9 @@ int tupan_cuda_kepler_dev(long long pairs, const void *const *arr, double dt, vo
 /* Sub-step doubling of the Kepler propagator (universal_kepler_solver.h:481-606: the reference
  * doubles without bound, 2^14 .. 2^27 sequential sub-steps for softened tight binaries).  Inside a
  * sakura sweep a pair gets 2^12 sub-steps; a pair that needs more is handed to a clean-up launch
- * (one thread per pair, up to 2^30 sub-steps, like the two-body entry point) whose result is added
+ * (one thread per pair, up to 2^27 sub-steps, like the two-body entry point) whose result is added
  * to the owner's outputs before the call's outputs count as written -- same answer as the
- * reference, the other pairs do not wait.  Only a pair that exceeds 2^30 is counted here: number of
+ * reference, the other pairs do not wait.  Only a pair that exceeds 2^27 is counted here: number of
  * such pairs since the last query (resets; synchronises the device); < 0 on error.  The
  * synchronous Part-1 entry points check it themselves and fail loudly. */
 long long tupan_cuda_kepler_limit_hits(void);

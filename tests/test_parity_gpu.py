@@ -116,7 +116,7 @@ def test_kepler_golden_in_place(prec):
 
     All 18 golden cases of the reference must match, the softened ones included: there the
     reference's energy check doubles the number of sub-steps without bound (2^14 .. 2^27 SEQUENTIAL
-    sub-steps in these vectors) and so does the two-body entry point (bound 2^30).  The one case
+    sub-steps in these vectors) and so does the two-body entry point (bound 2^27).  The one case
     that needs 2^27 sub-steps (43 s on a host core, minutes on one GPU thread) only runs with
     TUPAN_SLOW_TESTS=1; profiles/r02_kepler_softened.txt keeps its result."""
     import os

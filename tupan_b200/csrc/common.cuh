@@ -163,6 +163,20 @@ TUPAN_DEV float rcp_fast(float x)
 }
 
 TUPAN_DEV double rmax(double a, double b) { return fmax(a, b); }
+// max(acc, w) for a running maximum that starts at +0 and therefore never is negative: the
+// bit patterns of non-negative doubles order like the numbers, and any negative w (sign bit set) is
+// a negative integer, so a SIGNED 64-bit integer maximum is exactly fmax here -- two ISETP and two
+// SEL instead of DSETP (an FP64-pipe instruction) + FSEL + SEL + LOP3 + moves (tstep, ops.cuh).
+TUPAN_DEV double rmax_nonneg(double acc, double w)
+{
+    const long long a = __double_as_longlong(acc), b = __double_as_longlong(w);
+    return __longlong_as_double(a > b ? a : b);
+}
+TUPAN_DEV float rmax_nonneg(float acc, float w)
+{
+    const int a = __float_as_int(acc), b = __float_as_int(w);
+    return __int_as_float(a > b ? a : b);
+}
 TUPAN_DEV float rmax(float a, float b) { return fmaxf(a, b); }
 TUPAN_DEV double rsqrt_full(double a) { return 1.0 / sqrt(a); }
 TUPAN_DEV float rsqrt_full(float a) { return 1.0f / sqrtf(a); }

@@ -21,9 +21,10 @@
 //     hold 255 other threads of its CTA for minutes; a pair that runs into it is not failed but
 //     handed, with its description, to a clean-up launch (one thread per such pair, see
 //     sakura_cleanup_kernel) whose result is added to the owner's outputs afterwards;
-//   * the clean-up launch and the two-body entry point use 2^FULL_DOUBLINGS = 2^30 sub-steps, i.e.
-//     the reference's behaviour for anything it finishes within hours.  Only beyond that a pair is
-//     counted in kepler_limit_hits and the host entry points fail loudly (tupan_cuda_last_error).
+//   * the clean-up launch and the two-body entry point use 2^FULL_DOUBLINGS = 2^27 sub-steps -- the
+//     deepest case of the reference's golden vectors, 43 s on a host core -- i.e. the reference's
+//     behaviour for anything it finishes within minutes.  Only beyond that a pair is counted in
+//     kepler_limit_hits and the host entry points fail loudly (tupan_cuda_last_error).
 #pragma once
 #include "ops.cuh"
 
@@ -48,7 +49,9 @@ template <typename T> struct KeplerTol;
 template <> struct KeplerTol<double> { static TUPAN_DEV double value() { return 2.2737367544323205948e-13; } };  // 2^-42
 template <> struct KeplerTol<float>  { static TUPAN_DEV float value() { return 1.52587890625e-5f; } };           // 2^-16
 
-enum { KEPLER_MAXITER = 64, SWEEP_DOUBLINGS = 12, FULL_DOUBLINGS = 30 };
+// SOLVER_DOUBLINGS bounds the restart-on-solver-failure loop (:481-520), which in practice ends after
+// 0-3 doublings; it is what keeps a pair with a state the solver cannot digest from spinning.
+enum { KEPLER_MAXITER = 64, SWEEP_DOUBLINGS = 12, FULL_DOUBLINGS = 27, SOLVER_DOUBLINGS = 16 };
 
 __device__ unsigned int kepler_limit_hits = 0;   // pairs that ran into FULL_DOUBLINGS (this TU only)
 __device__ unsigned long long kepler_cleanup_total = 0;   // pairs the sweeps handed to the clean-up launch so far
@@ -61,7 +64,7 @@ template <typename T> struct State { T x, y, z, vx, vy, vz; };
 // needs several of them (sin/cos or sinh/cosh of the same argument).
 template <typename T> struct Stumpff { T c0, c1, c2, c3; };
 
-template <typename T> TUPAN_DEV Stumpff<T> stumpff(T z)
+template <typename T> TUPAN_DEV Stumpff<T> stumpff_plain(T z)
 {
     Stumpff<T> o;
     if (z < T(0)) {
@@ -88,6 +91,23 @@ template <typename T> TUPAN_DEV Stumpff<T> stumpff(T z)
 }
 
 template <typename T> struct KeplerEq { T dt, r0, rv0, m, alpha; };
+
+// fp64: the closed forms, exactly as the reference writes them (universal_kepler_solver.h:17-83).
+// fp32: (cos s - 1)/z and (sin s / s - 1)/z cancel catastrophically for the small arguments the
+// sub-stepping produces -- one ulp of cosf is 1e-3 of c2 at s = 0.01 -- which is the size of the
+// reference's own energy-check tolerance (64 x 2^-16): whether a softened orbit passes the check
+// then depends on the last bit of the libm in use (glibc's cosf on the host, CUDA's on the
+// device), and with CUDA's the doubling did not terminate for 9 of the 18 golden cases.  The fp32
+// library therefore evaluates the four functions in double and rounds once: the value the
+// reference's formula means, to float accuracy.
+TUPAN_DEV Stumpff<double> stumpff(double z) { return stumpff_plain<double>(z); }
+TUPAN_DEV Stumpff<float> stumpff(float z)
+{
+    const Stumpff<double> d = stumpff_plain<double>((double)z);
+    Stumpff<float> o;
+    o.c0 = (float)d.c0; o.c1 = (float)d.c1; o.c2 = (float)d.c2; o.c3 = (float)d.c3;
+    return o;
+}
 
 // Laguerre iteration, order 5 (universal_kepler_solver.h:219-254).
 template <typename T> TUPAN_DEV int laguerre5(T x0, T& x, const KeplerEq<T>& e)
@@ -176,6 +196,7 @@ template <typename T> TUPAN_DEV State<T> kepler_substep(T dt, T m, T e2, const S
     State<T> p = p0;
     int n = 1;
     bool bad = false;
+    if (max_doublings > SOLVER_DOUBLINGS) max_doublings = SOLVER_DOUBLINGS;
     for (int level = 0; level <= max_doublings; ++level) {
         bad = false;
         p = p0;

@@ -374,16 +374,20 @@ template <typename T> struct TstepOp {
         T x = r2 + (s[IE] + row[J8_E2]);
         T rv = rx * vx; rv = fma(ry, vy, rv); rv = fma(rz, vz, rv);
         T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
-        InvR<T> w = soft_inv<true>(x, r2);
+        // CLEAN = false (the seed's low word is not zeroed: one MOV less per rsqrt): a masked pair gets
+        // r1 ~ 1e-314 instead of 0, whose square r2inv underflows to exactly 0, so w2 = 0 * (v2 + phi2) = 0
+        // and gamma = 0 * (...) = 0 as before; w2 = 0 masks the second seed by its own exponent, and
+        // 0 * (a denormal) = 0.
+        InvR<T> w = soft_inv<false>(x, r2);
         // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv
         T phi2 = m2 * w.r1;
         T w2 = w.r2 * (v2 + phi2);
         T gamma = w.r2 * fma(w.r2, phi2, w2);
         // masked pair: w2 is exactly 0, its own exponent masks the seed -> gamma 0 -> w2 stays 0
-        gamma *= rsqrt_scaled<true>(w2, w2, p.eta, p.eta_k1, p.eta_k2);
+        gamma *= rsqrt_scaled<false>(w2, w2, p.eta, p.eta_k1, p.eta_k2);
         w2 = fma(-gamma, rv, w2);
         a[0] += w2;
-        a[1] = rmax(w2, a[1]);
+        a[1] = rmax_nonneg(a[1], w2);
     }
     static TUPAN_DEV void combine(T (&a)[NA], const T (&b)[NA])
     {

@@ -146,7 +146,7 @@ class _Lib(object):
 
     def check_async(self):
         """Failures of asynchronous device work that only leave a counter behind: a peer barrier of
-        the p2p transport that gave up waiting, a Kepler pair beyond 2^30 sub-steps.  Called where
+        the p2p transport that gave up waiting, a Kepler pair beyond 2^27 sub-steps.  Called where
         the integrators synchronise anyway (clock read-back, state download)."""
         hits = self.lib.tupan_cuda_peer_timeouts()
         if hits:
@@ -154,7 +154,7 @@ class _Lib(object):
                                          "trustworthy" % hits)
         hits = self.lib.tupan_cuda_kepler_limit_hits()
         if hits:
-            raise backend.TupanCudaError("%d Kepler pair(s) needed more than 2^30 sub-steps" % hits)
+            raise backend.TupanCudaError("%d Kepler pair(s) needed more than 2^27 sub-steps" % hits)
 
     @staticmethod
     def stream():
@@ -397,6 +397,19 @@ class Integrator(object):
         self.st.download(self.ps)
         self.L.check_async()
         return self.ps
+
+    def write_psdf(self, fname, fmode="a", with_potential=False):
+        """Append a snapshot of the device-resident state to a PSDF stream (tupan/io/psdfio.py:25-35;
+        tupan_b200/psdf.py): the columns go to the host with one copy each, straight from HBM."""
+        from .psdf import PSDFWriter
+        if self.world > 1:
+            raise NotImplementedError("snapshots of a sharded state: use particle_system (gathers) and PSDFWriter")
+        if with_potential:
+            self.force("phi_kernel", ("phi",))
+        cols = {k: v for k, v in self.st.t.items() if not (k.endswith("0") or k.startswith("_"))}
+        if not with_potential:
+            cols.pop("phi", None)
+        return PSDFWriter(fname).dump(cols, fmode=fmode, t=self.time)
 
     def energies(self):
         """(kinetic, potential) as particles/body.py:262-306 defines them, reduced on the device."""
