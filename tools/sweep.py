@@ -32,6 +32,7 @@ def main():
     ap.add_argument("hi", type=int, nargs="?", default=22)
     ap.add_argument("prec", nargs="?", default="float64")
     ap.add_argument("kernel", nargs="?", default="acc_jerk_kernel")
+    ap.add_argument("transport", nargs="?", default="auto", help="auto | nccl | p2p | p2p-graph")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -45,8 +46,9 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     scal = (1.0 / 64,) if args.kernel in ("tstep_kernel", "nreg_Xkernel", "nreg_Vkernel") else ()
     if rank == 0:
-        print("# %s %s on %d x %s; FMA-pipe peak measured in-process: %.2f TFLOP/s per GPU (%.0f MHz effective)"
-              % (args.kernel, args.prec, world, torch.cuda.get_device_name(dev), peak, mhz))
+        print("# %s %s on %d x %s, transport %s; FMA-pipe (3-register DFMA chain) probe in-process: %.2f TFLOP/s per "
+              "GPU (%.0f MHz effective)" % (args.kernel, args.prec, world, torch.cuda.get_device_name(dev),
+                                            args.transport, peak, mhz))
         print("# %8s %10s %12s %10s %8s %8s" % ("N", "ms", "Gpair/s", "TFLOP/s", "%peak", "per-GPU"))
     for p in range(args.lo, args.hi + 1):
         n = 1 << p
@@ -55,12 +57,16 @@ def main():
         for k in ("ax", "ay", "az", "jx", "jy", "jz"):
             full[k] = torch.zeros(n, dtype=dtype, device=dev)
         if world > 1:
-            sk = sharded.ShardedKernel(args.kernel, n, dtype, dev)
+            sk = sharded.ShardedKernel(args.kernel, n, dtype, dev, transport=args.transport.split("-")[0])
             mine = {a: full[a][sk.lo:sk.hi].contiguous() for a in device.KERNEL_INPUTS[args.kernel]}
             out = sk.evaluate(mine, scal)
+            graphed = args.transport.endswith("-graph") and sk.transport == "p2p"
 
             def step():
-                sk.evaluate(mine, scal, out)
+                if graphed:
+                    sk.evaluate_graphed(mine, scal, out)
+                else:
+                    sk.evaluate(mine, scal, out)
         else:
             out = device.run(args.kernel, full, full, scal)
 
@@ -89,8 +95,11 @@ def main():
         if rank == 0:
             pairs = float(n) * n / (ms * 1e-3)
             tf = pairs * FLOPS[args.kernel] * 1e-12
-            print("  %8d %10.3f %12.2f %10.2f %7.1f%% %8.2f" % (n, ms, pairs * 1e-9, tf, 100 * tf / (peak * world),
-                                                                pairs * 1e-9 / world), flush=True)
+            print("  %8d %10.3f %12.2f %10.2f %7.1f%% %8.2f  %s" % (n, ms, pairs * 1e-9, tf, 100 * tf / (peak * world),
+                                                                    pairs * 1e-9 / world,
+                                                                    sk.transport if world > 1 else "-"), flush=True)
+        if world > 1 and sk.transport == "p2p":
+            sk.check()
         del full, out
     if world > 1:
         dist.destroy_process_group()

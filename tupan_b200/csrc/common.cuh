@@ -1,8 +1,10 @@
 // common.cuh -- precision traits, softened inverse distances, sm_100a async-copy helpers.
 //
 // Part of tupan_b200: B200-native replacements for the pairwise kernels of ggf84/tupan
-// (reference: tupan/lib/src).  Nothing here is derived from the reference sources; the
-// reference lines cited in comments say which behaviour a routine has to reproduce.
+// (reference: tupan/lib/src).  The routines of THIS file are not derived from the reference
+// sources; the reference lines cited in comments say which behaviour a routine has to reproduce.
+// (Two files of the package do restate reference formulas closely and say so in their headers:
+// pn_ops.cuh -- the post-Newtonian polynomials -- and kepler.cuh -- the universal-variable solver.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(NT) pair_kernel_grouped(const __grid_constant_
 
     if (!MULTI) {
         // one buffer: every tile but possibly the last is full -- the hot loop has no case split
-        const int nfull = (int)((jhi - jlo) / TJ);
+        const long long span = jhi > jlo ? jhi - jlo : 0;       // a chunk beyond the end of the rows is empty
+        const int nfull = (int)(span / TJ);
         for (int t = 0; t < nfull; ++t) {
             const int s = t % STAGES;
             mbar_wait(&full[s], (unsigned)(t / STAGES) & 1u);
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(NT) pair_kernel_grouped(const __grid_constant_
         if (nfull < ntiles) {
             const int s = nfull % STAGES;
             mbar_wait(&full[s], (unsigned)(nfull / STAGES) & 1u);
-            plain_tile(tiles + s * TILE_ELEMS, (int)((jhi - jlo) - (long long)nfull * TJ));
+            plain_tile(tiles + s * TILE_ELEMS, (int)(span - (long long)nfull * TJ));
         }
     } else {
         for (int t = 0; t < ntiles; ++t) {

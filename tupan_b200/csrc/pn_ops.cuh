@@ -7,9 +7,19 @@
 // with k over the enabled orders.  The reference gates the orders with nested
 // `order > 1, > 3, > 4, > 5, > 6` tests (pn_terms.h:509-546; orders 1 and 3 add nothing);
 // here the gate is the template parameter LEVEL in {0, 2, 4, 5, 6, 7}, chosen on the host,
-// so each variant is straight-line code.  Coefficients are those of the harmonic-coordinate
-// two-body equations of motion through 3.5PN (Blanchet, Living Rev. Relativity), in the
-// general frame, with n = r_ij/r, vi, vj the two velocities, v = vi - vj.
+// so each variant is straight-line code.
+//
+// WHAT THIS FILE IS: the polynomials pn_1 .. pn_35 below RESTATE the reference's p2p_pn2 .. p2p_pn7
+// (pn_terms.h:126-470) term by term -- the same coefficients (those of the harmonic-coordinate
+// two-body equations of motion through 3.5PN, Blanchet, Living Rev. Relativity, general frame,
+// n = r_ij/r, vi, vj the two velocities, v = vi - vj), in the reference author's factorisation and
+// term order, with the scalar products renamed (njv2 -> nj2, ivjv -> vij, ...).  They were written
+// next to the reference source so that every term could be checked against it; they are not an
+// independent derivation.  What is new here is what surrounds them: one compiled variant per PN
+// level instead of run-time gates, the scalar products formed once per pair with FMAs, the masked
+// rsqrt of common.cuh, and the pair engine.  A re-derivation that shares sub-polynomials between
+// A and B and keeps the ~90 rational constants out of UMOV (107 of them per pair at level 7,
+// profiles/r01_static_instruction_mix_fp64.txt) is the open performance item of this kernel.
 //
 // flops/pair (binary operations counted in the reference source): 33 + 72 +
 // {16, 72, 16, 252, 171} for {1PN, 2PN, 2.5PN, 3PN, 3.5PN} -> 632 at order 7.

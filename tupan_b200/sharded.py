@@ -187,6 +187,8 @@ class ShardedKernel(object):
     # multi-owner kernel; launch- and tail-bound regime), above it with one launch per owner (the
     # single-buffer kernel is 3-4 % faster per pair: 1000 vs 958 Gpair/s at N = 2^20 on 2 GPUs)
     MULTI_MAX_PAIRS = 2.0e10
+    # "auto" transport: p2p below this many pairs per rank (profiles/r02_sweep_*_transports.txt)
+    AUTO_P2P_PAIRS = 4.0e9
 
     def __init__(self, kernel, n_total, dtype=torch.float64, device="cuda", group=None, engine=None,
                  overlap=True, transport=None, peer=None):
@@ -208,12 +210,21 @@ class ShardedKernel(object):
         self._partial = None
         self._width = None
         # "nccl": all-gather of the packed rows; "p2p": rows stay where they were packed and are
-        # read through peer mappings (GPUs of one node only)
-        self.transport = transport or os.environ.get("TUPAN_B200_TRANSPORT", "nccl")
-        if self.transport not in ("nccl", "p2p"):
-            raise ValueError("transport must be 'nccl' or 'p2p'")
+        # read through peer mappings (GPUs of one node only); "auto" (default): p2p with ONE
+        # multi-owner launch while the problem is latency-bound (fewer than AUTO_P2P_PAIRS pairs per
+        # rank: the all-gather's latency and the extra launches are what such sizes pay for), the
+        # all-gather above.  Every rank takes the same decision (it depends on n and the world size).
+        self.transport = transport or os.environ.get("TUPAN_B200_TRANSPORT", "auto")
+        if self.transport not in ("nccl", "p2p", "auto"):
+            raise ValueError("transport must be 'nccl', 'p2p' or 'auto'")
+        if self.transport == "auto":
+            small = float(self.rows_max) * self.n < self.AUTO_P2P_PAIRS
+            self.transport = "p2p" if (small and self.world > 1 and self.on_cuda and peer is None
+                                       and os.environ.get("TUPAN_B200_NO_P2P") is None) else "nccl"
         if self.world == 1 or not self.on_cuda:
             self.transport = "nccl"
+        self._graph = None
+        self._graph_key = None
         self.peer = peer               # injected by the CPU tests (rows gathered with gloo behind the same seam)
         if peer is not None:
             self.transport = "p2p"
@@ -317,6 +328,33 @@ class ShardedKernel(object):
         self._since_check = 0
         if self.peer is not None:
             self.peer.check()
+
+    def evaluate_graphed(self, local, scalars, out):
+        """The p2p evaluation replayed from a CUDA graph (pack, device-side barrier, one multi-owner
+        sweep, barrier, finalize: five launches whose latency is what a small problem costs).  The
+        tensors of `local` and `out` must be the same objects from call to call; the graph is
+        re-captured when they change.  Only for transport 'p2p' (no NCCL call inside)."""
+        if self.transport != "p2p":
+            return self.evaluate(local, scalars, out)
+        key = (tuple(t.data_ptr() for t in local.values()), tuple(t.data_ptr() for t in out.values()), tuple(scalars))
+        if self._graph is None or self._graph_key != key:
+            import gc
+            self.evaluate_p2p(local, scalars, out)           # eager once: buffers sized, peers mapped
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            gc.collect()
+            lib = self.engine.lib
+            before = lib.tupan_cuda_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.evaluate_p2p(local, scalars, out)
+            self._graph_launches = lib.tupan_cuda_launch_count() - before
+            lib.tupan_cuda_count_launches(-self._graph_launches)
+            self._graph, self._graph_key = g, key
+            dist.barrier(group=self.group)                   # every rank has its graph before anyone replays
+        self._graph.replay()
+        self.engine.lib.tupan_cuda_count_launches(self._graph_launches)
+        return out
 
     def evaluate(self, local, scalars=(), out=None):
         if self.transport == "p2p":
