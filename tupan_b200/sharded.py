@@ -187,8 +187,12 @@ class ShardedKernel(object):
     # multi-owner kernel; launch- and tail-bound regime), above it with one launch per owner (the
     # single-buffer kernel is 3-4 % faster per pair: 1000 vs 958 Gpair/s at N = 2^20 on 2 GPUs)
     MULTI_MAX_PAIRS = 2.0e10
-    # "auto" transport: p2p below this many pairs per rank (profiles/r02_sweep_*_transports.txt)
-    AUTO_P2P_PAIRS = 4.0e9
+    # "auto" transport: p2p below this many pairs per rank.  0 = never: with the round-2 launch
+    # plan the all-gather path is at least as fast as reading the rows in place at EVERY size on 2
+    # and on 8 GPUs (profiles/r02_sweep_accjerk_fp64_n{2,8}_transports.txt: N = 16384 on 8 GPUs
+    # 2130 Gpair/s over NCCL, 2083 with the graph-replayed peer sweep; N = 65536 3751 vs 3641), so
+    # the peer transport stays an option (TUPAN_B200_TRANSPORT=p2p) and is not chosen on its own.
+    AUTO_P2P_PAIRS = 0.0
 
     def __init__(self, kernel, n_total, dtype=torch.float64, device="cuda", group=None, engine=None,
                  overlap=True, transport=None, peer=None):
