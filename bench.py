@@ -47,14 +47,14 @@ DP_INSTR_PER_PAIR = 32       # FP64-pipe instructions our kernel issues per pair
 S8 = ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz")
 OUT6 = ("ax", "ay", "az", "jx", "jy", "jz")
 METRIC = "acc_jerk pair-interactions/s fp64"
-# dram__bytes_read.sum + dram__bytes_write.sum of the pair kernel, per launch, from the one
-# `ncu --set full` capture of this command (profiles/r01_accjerk_v4_n1m_ncu_summary.txt):
-# 1.568 GB read + 1.358 GB written at N = 2^20 on one GPU.  It exceeds the 184.5 MB of
-# algorithmic bytes because the j range is split into 25 chunks for wave balance (each chunk
-# re-reads the i-state and writes a partial accumulator slot); at 1.3 GB/s it is 0.02 % of HBM
-# bandwidth -- this kernel is FP64-pipe bound.
-# keyed by (n, GPUs, j-chunks of the launch)
-NCU_TRAFFIC = {(1 << 20, 1, 25): 1567549000 + 1357939000}
+# dram__bytes_read.sum + dram__bytes_write.sum of the pair kernel, per launch, from ncu captures of
+# this command, keyed by (n, GPUs, j-chunks of the launch):
+#   round 2, grouped kernel, 32 chunks (profiles/r02_accjerk_grouped_n1m_dram.csv): 1.944 GB + 1.686 GB
+#   round 1, 25 chunks (profiles/r01_accjerk_v4_n1m_ncu_summary.txt): 1.568 GB + 1.358 GB
+# It exceeds the 184.5 MB of algorithmic bytes because the j range is split into chunks for wave
+# balance (each chunk writes a partial accumulator slot that finalize reads back); at 1.7 GB/s it is
+# 0.03 % of HBM bandwidth -- this kernel is FP64-pipe bound.
+NCU_TRAFFIC = {(1 << 20, 1, 32): 1944071168 + 1686260480, (1 << 20, 1, 25): 1567549000 + 1357939000}
 KERNEL_NAME = "pair_kernel_grouped<AccJerkOp<double>>"
 PARITY_TOL = 1e-12           # BASELINE.json north_star: ~1e-12 in fp64 (summation order differs)
 PARITY_SAMPLE = 256          # i-particles per rank checked against the full j-set
