@@ -32,6 +32,17 @@ template <typename T> struct PNParams { T c2, c4, c5, c6, c7; };
 
 template <typename T> TUPAN_DEV constexpr T fr(int n, int d) { return T(n) / T(d); }
 
+// The rational coefficients whose denominators are not powers of two (x/3, /5, /7, /15, /21, /35,
+// /105 ...) need all 64 bits: as literals ptxas materialises each of them with two UMOVs into a
+// uniform register, per pair (107 UMOVs per pair at level 7, profiles/r01_static_instruction_mix_fp64.txt).
+// As __constant__ objects they are constant-bank operands of the DFMA / DMUL that uses them.
+template <int N, int D> __constant__ double pnk_d = double(N) / double(D);
+template <int N, int D> __constant__ float pnk_f = float(N) / float(D);
+template <typename T, int N, int D> struct PNK;
+template <int N, int D> struct PNK<double, N, D> { static TUPAN_DEV double v() { return pnk_d<N, D>; } };
+template <int N, int D> struct PNK<float, N, D> { static TUPAN_DEV float v() { return pnk_f<N, D>; } };
+#define FRK(n, d) (PNK<T, (n), (d)>::v())
+
 template <typename T> struct PNScalars {
     T mi, mj, mi2, mj2, mimj, ir, ir2;
     T v2, vi2, vj2, vi4, vj4, vij, vij2;
@@ -67,8 +78,8 @@ template <typename T> TUPAN_DEV void pn_2(const PNScalars<T>& q, T c4, T& A, T& 
 // ---- 2.5PN ------------------------------------------------------------------------------
 template <typename T> TUPAN_DEV void pn_25(const PNScalars<T>& q, T c5, T& A, T& B)
 {
-    T a = q.nv * (q.ir * (-fr<T>(24, 5) * q.mi + fr<T>(208, 15) * q.mj) + fr<T>(12, 5) * q.v2);
-    T b = -q.v2 + q.ir * (fr<T>(8, 5) * q.mi - fr<T>(32, 5) * q.mj);
+    T a = q.nv * (q.ir * (-FRK(24, 5) * q.mi + FRK(208, 15) * q.mj) + FRK(12, 5) * q.v2);
+    T b = -q.v2 + q.ir * (FRK(8, 5) * q.mi - FRK(32, 5) * q.mj);
     T s = (q.mi * q.ir) * c5;
     A += a * s;
     B += b * s;
@@ -104,9 +115,9 @@ template <typename T> TUPAN_DEV void pn_3(const PNScalars<T>& q, T c6, T& A, T& 
         + mi2 * ir2 * (-fr<T>(2069, 8) * ni2 + T(543) * ninj - fr<T>(939, 4) * nj2 + fr<T>(471, 8) * vi2
                        + fr<T>(357, 8) * (vj2 - T(2) * vij))
         + ir * ir2 * (T(16) * mj * mj2
-                      + mi2 * mj * (fr<T>(547, 3) - fr<T>(41, 16) * PI2)
-                      - fr<T>(13, 12) * mi * mi2
-                      + mi * mj2 * (fr<T>(545, 3) - fr<T>(41, 16) * PI2));
+                      + mi2 * mj * (FRK(547, 3) - fr<T>(41, 16) * PI2)
+                      - FRK(13, 12) * mi * mi2
+                      + mi * mj2 * (FRK(545, 3) - fr<T>(41, 16) * PI2));
 
     T b = nj * (vj2 * (vi2 + T(8) * vij - T(7) * vj2) - T(2) * vij2
                 + nj * (T(6) * ni * (vij - T(2) * vj2)
@@ -117,7 +128,7 @@ template <typename T> TUPAN_DEV void pn_3(const PNScalars<T>& q, T c6, T& A, T& 
                      + T(2) * ni * (vij - vj2))
         + mi * ir * (ni * (fr<T>(207, 8) * vi2 + fr<T>(81, 8) * vj2 - T(36) * vij - fr<T>(269, 4) * nj2
                            + ni * (fr<T>(565, 4) * nj - fr<T>(243, 4) * ni))
-                     + nj * (fr<T>(83, 8) * vj2 + fr<T>(27, 4) * vij - fr<T>(137, 8) * vi2 - fr<T>(95, 12) * nj2))
+                     + nj * (fr<T>(83, 8) * vj2 + fr<T>(27, 4) * vij - fr<T>(137, 8) * vi2 - FRK(95, 12) * nj2))
         + ir2 * (mj2 * (T(4) * ni + T(5) * nj)
                  + mi2 * (fr<T>(311, 4) * ni - fr<T>(357, 4) * nj)
                  + mimj * (fr<T>(479, 8) * nj - fr<T>(307, 8) * ni + fr<T>(123, 32) * PI2 * nv));
@@ -132,34 +143,34 @@ template <typename T> TUPAN_DEV void pn_35(const PNScalars<T>& q, T c7, T& A, T&
     const T v2 = q.v2, vi2 = q.vi2, vj2 = q.vj2, vi4 = q.vi4, vj4 = q.vj4, vij = q.vij;
     const T nv = q.nv, nv2 = q.nv2, ni = q.ni, nj = q.nj, ni2 = q.ni2, nj2 = q.nj2, ninj = q.ninj;
 
-    T a = mi2 * ir2 * (fr<T>(3992, 105) * ni - fr<T>(4328, 105) * nj)
-        + mimj * ir * ir2 * (-fr<T>(13576, 105) * ni + fr<T>(2872, 21) * nj)
-        + mj2 * ir * ir2 * (-fr<T>(3172, 21) * nv)
-        + mi * ir * (ni * (T(48) * ni2 - fr<T>(4888, 105) * vi2 + fr<T>(2056, 21) * vij - fr<T>(1028, 21) * vj2)
-                     + ninj * (-fr<T>(696, 5) * ni + fr<T>(744, 5) * nj)
-                     + nj * (-fr<T>(288, 5) * nj2 + fr<T>(5056, 105) * vi2 - fr<T>(2224, 21) * vij
-                             + fr<T>(5812, 105) * vj2))
-        + mj * ir * (ni * (-fr<T>(582, 5) * ni2 - fr<T>(2864, 35) * vij + fr<T>(1432, 35) * vj2)
-                     + ninj * (fr<T>(1746, 5) * ni - fr<T>(1954, 5) * nj)
-                     + fr<T>(3568, 105) * nv * vi2
-                     + nj * (T(158) * nj2 - fr<T>(5752, 105) * vj2 + fr<T>(10048, 105) * vij))
-        + (nv * (T(-56) * nv2 * nv2 - fr<T>(246, 35) * vi4)
+    T a = mi2 * ir2 * (FRK(3992, 105) * ni - FRK(4328, 105) * nj)
+        + mimj * ir * ir2 * (-FRK(13576, 105) * ni + FRK(2872, 21) * nj)
+        + mj2 * ir * ir2 * (-FRK(3172, 21) * nv)
+        + mi * ir * (ni * (T(48) * ni2 - FRK(4888, 105) * vi2 + FRK(2056, 21) * vij - FRK(1028, 21) * vj2)
+                     + ninj * (-FRK(696, 5) * ni + FRK(744, 5) * nj)
+                     + nj * (-FRK(288, 5) * nj2 + FRK(5056, 105) * vi2 - FRK(2224, 21) * vij
+                             + FRK(5812, 105) * vj2))
+        + mj * ir * (ni * (-FRK(582, 5) * ni2 - FRK(2864, 35) * vij + FRK(1432, 35) * vj2)
+                     + ninj * (FRK(1746, 5) * ni - FRK(1954, 5) * nj)
+                     + FRK(3568, 105) * nv * vi2
+                     + nj * (T(158) * nj2 - FRK(5752, 105) * vj2 + FRK(10048, 105) * vij))
+        + (nv * (T(-56) * nv2 * nv2 - FRK(246, 35) * vi4)
            + ni * (v2 * (T(60) * ni2 - T(180) * ninj + T(174) * nj2)
-                   + vij * (fr<T>(1068, 35) * (vi2 - vij) + fr<T>(984, 35) * vj2)
-                   - fr<T>(534, 35) * vi2 * vj2 - fr<T>(204, 35) * vj4)
+                   + vij * (FRK(1068, 35) * (vi2 - vij) + FRK(984, 35) * vj2)
+                   - FRK(534, 35) * vi2 * vj2 - FRK(204, 35) * vj4)
            + nj * (T(-54) * nj2 * v2
-                   + vij * (-fr<T>(984, 35) * vi2 + fr<T>(180, 7) * vij - fr<T>(732, 35) * vj2)
-                   + fr<T>(90, 7) * vi2 * vj2 + fr<T>(24, 7) * vj4));
+                   + vij * (-FRK(984, 35) * vi2 + FRK(180, 7) * vij - FRK(732, 35) * vj2)
+                   + FRK(90, 7) * vi2 * vj2 + FRK(24, 7) * vj4));
 
-    T b = -mi2 * ir2 * fr<T>(184, 21) + mimj * ir2 * fr<T>(6224, 105) + mj2 * ir2 * fr<T>(6388, 105)
-        + mi * ir * (fr<T>(52, 15) * ni2 - fr<T>(56, 15) * ninj - fr<T>(44, 15) * nj2 - fr<T>(132, 35) * vi2
-                     + fr<T>(152, 35) * vij - fr<T>(48, 35) * vj2)
-        + mj * ir * (fr<T>(454, 15) * ni2 - fr<T>(372, 5) * ninj + fr<T>(854, 15) * nj2 - fr<T>(152, 21) * vi2
-                     + fr<T>(2864, 105) * vij - fr<T>(1768, 105) * vj2)
-        + (T(60) * nv2 * nv2 + v2 * (-fr<T>(348, 5) * ni2 + fr<T>(684, 5) * ninj - T(66) * nj2)
-           + fr<T>(334, 35) * vi4
-           + vij * (-fr<T>(1336, 35) * vi2 + fr<T>(1308, 35) * vij - fr<T>(1252, 35) * vj2)
-           + fr<T>(654, 35) * vi2 * vj2 + fr<T>(292, 35) * vj4);
+    T b = -mi2 * ir2 * FRK(184, 21) + mimj * ir2 * FRK(6224, 105) + mj2 * ir2 * FRK(6388, 105)
+        + mi * ir * (FRK(52, 15) * ni2 - FRK(56, 15) * ninj - FRK(44, 15) * nj2 - FRK(132, 35) * vi2
+                     + FRK(152, 35) * vij - FRK(48, 35) * vj2)
+        + mj * ir * (FRK(454, 15) * ni2 - FRK(372, 5) * ninj + FRK(854, 15) * nj2 - FRK(152, 21) * vi2
+                     + FRK(2864, 105) * vij - FRK(1768, 105) * vj2)
+        + (T(60) * nv2 * nv2 + v2 * (-FRK(348, 5) * ni2 + FRK(684, 5) * ninj - T(66) * nj2)
+           + FRK(334, 35) * vi4
+           + vij * (-FRK(1336, 35) * vi2 + FRK(1308, 35) * vij - FRK(1252, 35) * vj2)
+           + FRK(654, 35) * vi2 * vj2 + FRK(292, 35) * vj4);
     T s = (mi * ir) * c7;
     A += a * s;
     B += b * s;
