@@ -1,4 +1,4 @@
-// k_newton.cu -- phi, acc, acc_jerk, tstep on the pair engine.
+// k_newton.cu -- phi, acc, tstep on the pair engine (acc_jerk: k_accjerk.cu).
 #include "ops.cuh"
 #include "runtime.cuh"
 
@@ -14,6 +14,5 @@ static inline TstepParams<real_t> tstep_params(const double* s)
 }
 TUPAN_DEFINE_VTABLE(vt_phi, PhiOp<real_t>, "phi_kernel", 5, 1, 0, 14, no_params)
 TUPAN_DEFINE_VTABLE(vt_acc, AccOp<real_t>, "acc_kernel", 5, 3, 0, 20, no_params)
-TUPAN_DEFINE_VTABLE(vt_acc_jerk, AccJerkOp<real_t>, "acc_jerk_kernel", 8, 6, 0, 42, no_params)
 TUPAN_DEFINE_VTABLE(vt_tstep, TstepOp<real_t>, "tstep_kernel", 8, 2, 1, 42, tstep_params)
 }  // namespace tupan
