@@ -11,7 +11,7 @@ CASES = (("acc_jerk_kernel", ()), ("tstep_kernel", (1.0 / 64,)), ("phi_kernel", 
          ("sakura_kernel", (1.0 / 256, 1)), ("pnacc_kernel", (7,) + tuple(128.0 ** -k for k in range(1, 8))))
 
 
-@pytest.mark.parametrize("plan", ((-1, 0, 1), (0, 0, 1), (0, 0, 5), (1, 0, 3), (1, 3, 2), (1, 5, 1)))
+@pytest.mark.parametrize("plan", ((-1, 0, 1), (0, 0, 1), (0, 0, 5), (2, 0, 5), (1, 0, 3), (1, 3, 2), (1, 5, 1)))
 def test_multi_owner_sweep_equals_single_buffer(plan):
     import torch
     from tupan_b200 import backend, device, ics, sharded

@@ -37,8 +37,9 @@ PRECS = ("float64", "float32")
 TOL = {"float64": 1e-12, "float32": 1e-5}
 TOL_SOLVER = {"float64": 1e-10, "float32": 1e-3}
 # launch plans (lane_split, js_log2, jg): automatic, i-per-thread, lane split x1/x8/x32 with
-# j chunks, i-per-thread with j chunks.  Every plan must give the same answer.
-PLANS = ((-1, 0, 1), (0, 0, 1), (1, 0, 1), (1, 3, 1), (1, 5, 3), (0, 0, 2))
+# j chunks, i-per-thread with j chunks, the second group shape of the grouped kernels (2; kernels
+# without one run shape 0).  Every plan must give the same answer.
+PLANS = ((-1, 0, 1), (0, 0, 1), (1, 0, 1), (1, 3, 1), (1, 5, 3), (0, 0, 2), (2, 0, 1), (2, 0, 3))
 
 
 def tol_for(name, prec):

@@ -27,10 +27,12 @@ def test_every_kernel_gets_a_valid_plan(prec):
         for ni, nj in ((1, 1), (2, 2), (3, 1000), (1000, 3), (100, 100), (1024, 1024), (5000, 40001),
                        (65536, 65536), (4096, 1 << 20), (1 << 20, 1 << 20), (131072, 1 << 20)):
             split, js, jg = query(lib, kernel, ni, nj, scal.get(kernel, ()))
-            assert split in (0, 1) and 0 <= js <= 5 and 1 <= jg <= 64, (kernel, ni, nj, split, js, jg)
+            assert split in (0, 1, 2) and 0 <= js <= 5 and 1 <= jg <= 64, (kernel, ni, nj, split, js, jg)
             assert jg <= max(1, (nj + 127) // 128), "a chunk holds at least one tile"
-            if not split:
+            if split != 1:
                 assert js == 0
+            if split == 2:                       # only kernels with a second group shape may be given it
+                assert kernel == "acc_jerk_kernel" and prec == "float64"
 
 
 def test_acc_jerk_fp64_shapes_follow_the_measurements():
@@ -39,13 +41,15 @@ def test_acc_jerk_fp64_shapes_follow_the_measurements():
     for n in (2, 64, 512, 1024):
         split, js, jg = query(lib, "acc_jerk_kernel", n, n)
         assert split == 1 and js >= 3, (n, split, js, jg)
-    # N = 4096: 16 chunks x 8 i-blocks on 128 SMs (57 us; the 32-lane split took 190 us)
+    # N = 4096: 16 chunks x 8 i-blocks of 512 on 128 SMs (57 us; the 32-lane split took 190 us) -- the
+    # second group shape (2): i-blocks of 768 would leave a third of the last block empty
     split, js, jg = query(lib, "acc_jerk_kernel", 4096, 4096)
-    assert split == 0 and 8 <= jg <= 32
+    assert split == 2 and 8 <= jg <= 32
     # N = 16384: best measured 32 chunks; 9 chunks (two 15-tile CTAs on most SMs) was 5 % slower
     split, js, jg = query(lib, "acc_jerk_kernel", 16384, 16384)
-    assert split == 0 and jg >= 16
-    # large N and the 8-GPU shard of N = 2^20: throughput shape, enough chunks to level the SMs
+    assert split == 2 and jg >= 16
+    # large N and the 8-GPU shard of N = 2^20: the 3 x 2 shape (768 particles per CTA), enough chunks to
+    # level the SMs (1366 i-blocks x 17 chunks = 156.9 CTAs per SM)
     for ni in (1 << 20, 131072):
         split, js, jg = query(lib, "acc_jerk_kernel", ni, 1 << 20)
         assert split == 0 and jg >= 8

@@ -173,15 +173,21 @@ template <typename T> struct AccJerkOp {
     //   2   v' = v - alpha r for every pair, then per pair g = -(m q3) and the six accumulations,
     //       all with g as the LAST-defined multiplicand (ptxas puts the operand it shares between
     //       consecutive DFMAs in one slot when it is the later-defined one).
-    // Measured (profiles/r02_kernel_lab_grouped.txt): 3.2 uncached three-register DFMAs per pair
-    // instead of 9.3, 72.3 instead of 77.2 clocks per pair in the lab kernel.
+    // Measured (profiles/r02_kernel_lab_grouped.txt, r02_kernel_lab3_w3.txt): W x U = 3 x 2 leaves 2.0
+    // uncached three-register DFMAs per pair (the first of each run of DFMAs that share an operand)
+    // instead of 9.3, and 5.8 instead of 6.9 non-FP64 instructions per pair: 71.4 clocks per pair in
+    // the lab kernel (round-1 kernel 75.1, 2 x 4 with one-trip loops 72.9).
 #ifndef TUPAN_AJ_GW
-#define TUPAN_AJ_GW 2
-#define TUPAN_AJ_GU 4
+#define TUPAN_AJ_GW 3
+#define TUPAN_AJ_GU 2
 #define TUPAN_AJ_GNT 256
 #endif
-    // GMODE bit 0: block 1a on its own; bit 1: g formed in block 2 (see above)
-    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT, GMODE = 3 };
+    // GMODE bit 0: block 1a on its own; bit 1: g formed in block 2 (see above); bit 2: block 2 pair by
+    // pair; bit 3: the blocks are fenced by `if (one != 0)` instead of one-trip loops (two uniform
+    // branches per group instead of two loop headers with their counters)
+    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT, GMODE = 11 };
+    // second shape, 2 x 4 (512 instead of 768 particles per CTA; 72.9 clocks per pair): small and medium ni
+    enum { GALT = 1, GW2 = 2, GU2 = 4, GMODE2 = 11, GCOST2_PERMILLE = 1021 };
     struct PV { T rx, ry, rz, vx, vy, vz, na, q3, mj; };
     template <int W, int U, int MODE>
     static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int one)
@@ -197,14 +203,19 @@ template <typename T> struct AccJerkOp {
             e[p] = si[IE] + rw[J8_E2];
             o[p].mj = rw[JM];
         }
-#pragma unroll 1
-        for (int z = 0; z < ((MODE & 1) ? one : 1); ++z) {       // block 1a
+        auto chains = [&]() {
 #pragma unroll
             for (int p = 0; p < G; ++p) { r2[p] = o[p].rx * o[p].rx; rv[p] = o[p].rx * o[p].vx; }
 #pragma unroll
             for (int p = 0; p < G; ++p) { r2[p] = fma(o[p].ry, o[p].ry, r2[p]); rv[p] = fma(o[p].ry, o[p].vy, rv[p]); }
 #pragma unroll
             for (int p = 0; p < G; ++p) { r2[p] = fma(o[p].rz, o[p].rz, r2[p]); rv[p] = fma(o[p].rz, o[p].vz, rv[p]); }
+        };
+        if (MODE & 8) {                 // block 1a behind a never-skipped branch (cheaper than a loop)
+            if (one != 0) chains();
+        } else {
+#pragma unroll 1
+            for (int z = 0; z < ((MODE & 1) ? one : 1); ++z) chains();       // block 1a
         }
 #pragma unroll
         for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x = r2 + e2
@@ -351,7 +362,7 @@ template <typename T> struct SnapCrackleOp {
 #define TUPAN_SC_GROUPED 1
 #endif
     enum { GROUPED = (TUPAN_SC_GROUPED != 0 && sizeof(T) == 8), GW = TUPAN_SC_GW, GU = TUPAN_SC_GU, GNT = TUPAN_SC_GNT,
-           GMODE = 1 };
+           GMODE = 1, GALT = 0 };
     struct PV { T rx, ry, rz, vx, vy, vz, ax, ay, az, jx, jy, jz, al, a2, be, al3, be3, ga, g; };
     template <int W, int U, int MODE>
     static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int one)

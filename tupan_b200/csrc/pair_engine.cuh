@@ -316,12 +316,18 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
 //                                          kernel's one-trip loop)
 // Partial tiles (the end of a j range) take Op::pair row by row.
 // ---------------------------------------------------------------------------------------
-template <class Op, typename = void> struct Grouped { enum { value = 0, W = 1, U = 1, NT = 256 }; };
+template <class Op, typename = void> struct Grouped { enum { value = 0, W = 1, U = 1, NT = 256, MODE = 0 }; };
 template <class Op> struct Grouped<Op, typename std::enable_if<(Op::GROUPED != 0)>::type> {
-    enum { value = 1, W = Op::GW, U = Op::GU, NT = Op::GNT };
+    enum { value = 1, W = Op::GW, U = Op::GU, NT = Op::GNT, MODE = Op::GMODE };
+};
+// A second group shape (Op::GALT: GW2 x GU2, GMODE2) with fewer particles per CTA: the launch plan takes
+// it where the first shape's i-blocks would leave SMs idle or half-filled (small and medium ni).
+template <class Op, typename = void> struct GroupedAlt { enum { value = 0, W = 1, U = 1, MODE = 0, COST_PERMILLE = 1000 }; };
+template <class Op> struct GroupedAlt<Op, typename std::enable_if<(Op::GROUPED != 0 && Op::GALT != 0)>::type> {
+    enum { value = 1, W = Op::GW2, U = Op::GU2, MODE = Op::GMODE2, COST_PERMILLE = Op::GCOST2_PERMILLE };
 };
 
-template <class Op, int NT, int W, int U, int TJ, int STAGES, bool MULTI = false>
+template <class Op, int NT, int W, int U, int MODE, int TJ, int STAGES, bool MULTI = false>
 __global__ void __launch_bounds__(NT) pair_kernel_grouped(const __grid_constant__ PairArgs<Op> a)
 {
     typedef typename Op::real T;
@@ -379,9 +385,13 @@ __global__ void __launch_bounds__(NT) pair_kernel_grouped(const __grid_constant_
             typename Op::PV pv[G];
 #pragma unroll
             for (int u = 0; u < U; ++u) load_row<Op>(sj + (j + u) * NJP, rows[u]);
-            Op::template group_phase1<W, U, Op::GMODE>(is, rows, pv, a.prm, one);
+            Op::template group_phase1<W, U, MODE>(is, rows, pv, a.prm, one);
+            if (MODE & 8) {             // block 2 behind a never-skipped branch (cheaper than a one-trip loop)
+                if (one != 0) Op::template group_phase2<W, U, MODE>(pv, acc, a.prm);
+            } else {
 #pragma unroll 1
-            for (int z = 0; z < one; ++z) Op::template group_phase2<W, U, Op::GMODE>(pv, acc, a.prm);
+                for (int z = 0; z < one; ++z) Op::template group_phase2<W, U, MODE>(pv, acc, a.prm);
+            }
         }
     };
     auto plain_tile = [&](const T* sj, int cnt) {
@@ -658,11 +668,13 @@ __global__ void __launch_bounds__(NT, 2) pair_kernel_defer(const __grid_constant
 // The kernel an Op runs on: <throughput shape> and <lane split>.
 template <class Op, bool LANE_SPLIT> struct KernelOf {
     typedef void (*Fn)(const PairArgs<Op>);
-    template <int NT, int TJ, int STAGES, bool MULTI = false> static Fn get()
+    template <int NT, int TJ, int STAGES, bool MULTI = false, bool ALT = false> static Fn get()
     {
         if constexpr (Defers<Op>::value != 0) return pair_kernel_defer<Op, NT, TJ, STAGES, LANE_SPLIT, MULTI>;
+        else if constexpr (!LANE_SPLIT && Grouped<Op>::value != 0 && ALT && GroupedAlt<Op>::value != 0)
+            return pair_kernel_grouped<Op, NT, GroupedAlt<Op>::W, GroupedAlt<Op>::U, GroupedAlt<Op>::MODE, TJ, STAGES, MULTI>;
         else if constexpr (!LANE_SPLIT && Grouped<Op>::value != 0)
-            return pair_kernel_grouped<Op, NT, Grouped<Op>::W, Grouped<Op>::U, TJ, STAGES, MULTI>;
+            return pair_kernel_grouped<Op, NT, Grouped<Op>::W, Grouped<Op>::U, Grouped<Op>::MODE, TJ, STAGES, MULTI>;
         else return pair_kernel<Op, NT, LANE_SPLIT ? 1 : Op::WPT, TJ, STAGES, LANE_SPLIT, MULTI>;
     }
 };
@@ -694,7 +706,8 @@ __global__ void finalize_kernel(InRefs<typename Op::real> iarr, long long ni,
 // Host side: launch plan and launcher.
 // ---------------------------------------------------------------------------------------
 struct Plan {
-    int lane_split;  // 0: WPT particles per thread, lanes independent; 1: JS lanes per particle
+    int lane_split;  // 0: WPT particles per thread, lanes independent; 1: JS lanes per particle;
+                     // 2: as 0 with the Op's second group shape (GroupedAlt; ops without one run 0)
     int js_log2;     // lane-split only
     int jg;          // number of j chunks over blockIdx.y (>1 -> workspace + finalize)
 };
@@ -708,6 +721,8 @@ template <class Op> struct Tune {
         TJ = 128, STAGES = 4, NT_SPLIT = 128,
         NT = Grouped<Op>::value ? (int)Grouped<Op>::NT : 256,                 // throughput shape
         WPT = Grouped<Op>::value ? (int)Grouped<Op>::W : (Defers<Op>::value ? 1 : (int)Op::WPT),
+        ALT = Grouped<Op>::value && GroupedAlt<Op>::value,                    // second throughput shape
+        WPT2 = ALT ? (int)GroupedAlt<Op>::W : WPT,
         SMEM = (int)PairSmemDefer<Op, NT, TJ, STAGES>::BYTES
     };
 };
@@ -749,10 +764,12 @@ inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
     };
     double best = 1e300;
 
-    {   // throughput shape
-        const long long IB = (long long)U::NT * U::WPT;
+    for (int shape = 0; shape <= (U::ALT ? 1 : 0); ++shape) {   // throughput shape(s)
+        const int wpt = shape ? (int)U::WPT2 : (int)U::WPT;
+        const double cost = shape ? GroupedAlt<Op>::COST_PERMILLE * 1e-3 : 1.0;
+        const long long IB = (long long)U::NT * wpt;
         const long long iblocks = (ni + IB - 1) / IB;
-        const double tile_us = (double)TJ * U::WPT * cpw * ((double)U::NT / 32 / 4) / clk_per_us;
+        const double tile_us = (double)TJ * wpt * cpw * cost * ((double)U::NT / 32 / 4) / clk_per_us;
         const long long maxg = tiles < 64 ? tiles : 64;
         for (long long g = 1; g <= maxg; ++g) {
             const long long tpc = (tiles + g - 1) / g;            // tiles per chunk
@@ -763,7 +780,7 @@ inline Plan choose_plan(const DeviceInfo& dev, long long ni, long long nj)
             // equal CTAs handed out greedily: the busiest SM runs ceil(CTAs / SMs) of them
             const double busiest = per_sm * (tpc + 0.1);       // + prologue/epilogue of each CTA
             const double t = 8.0 + busiest * tile_us + finalize_us(chunks);
-            if (t < best) { best = t; best_plan.lane_split = 0; best_plan.js_log2 = 0; best_plan.jg = (int)g; }
+            if (t < best) { best = t; best_plan.lane_split = shape ? 2 : 0; best_plan.js_log2 = 0; best_plan.jg = (int)g; }
         }
     }
     for (int js = 0; js <= 5 && (TJ >> js) >= 4; ++js) {          // lane split
@@ -826,19 +843,22 @@ inline cudaError_t launch_pairs(const Plan& plan, const InRefs<typename Op::real
     cudaGetDevice(&dev_id);
     const bool multi = seg != nullptr;
     // function attributes are per device and per instantiation
-    static int attr_device[4] = {-1, -1, -1, -1};
+    static int attr_device[6] = {-1, -1, -1, -1, -1, -1};
     auto prepare = [&](typename KernelOf<Op, false>::Fn k, size_t smem, int which) {
         if (attr_device[which] != dev_id) {
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_device[which] = dev_id;
         }
     };
-    if (!plan.lane_split) {
-        auto k = multi ? KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, true>()
-                       : KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, false>();
+    if (plan.lane_split != 1) {
+        const bool alt = plan.lane_split == 2 && U::ALT;
+        auto k = alt ? (multi ? KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, true, true>()
+                              : KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, false, true>())
+                     : (multi ? KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, true>()
+                              : KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, false>());
         const size_t smem = U::SMEM;
-        prepare(k, smem, multi ? 1 : 0);
-        const long long per_cta = (long long)U::NT * U::WPT;
+        prepare(k, smem, (alt ? 4 : 0) + (multi ? 1 : 0));
+        const long long per_cta = (long long)U::NT * (alt ? (int)U::WPT2 : (int)U::WPT);
         dim3 grid((unsigned)((ni + per_cta - 1) / per_cta), (unsigned)plan.jg);
         k<<<grid, U::NT, smem, stream>>>(a);
     } else {

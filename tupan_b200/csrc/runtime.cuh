@@ -196,7 +196,7 @@ template <class Op> struct Runner {
         if (p.jg < 1) p.jg = 1;
         if (p.js_log2 < 0) p.js_log2 = 0;
         if (p.js_log2 > 5) p.js_log2 = 5;
-        if (!p.lane_split) p.js_log2 = 0;
+        if (p.lane_split != 1) p.js_log2 = 0;
         return p;
     }
 
