@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 FLOPS_PER_PAIR = 42          # acc_jerk_kernel_common.h:56 "Total flop count: 42"
-DP_INSTR_PER_PAIR = 32       # FP64-pipe instructions our kernel issues per pair (SASS count)
+DP_INSTR_PER_PAIR = 31       # FP64-pipe instructions our kernel issues per pair (SASS count)
 S8 = ("mass", "rx", "ry", "rz", "eps2", "vx", "vy", "vz")
 OUT6 = ("ax", "ay", "az", "jx", "jy", "jz")
 METRIC = "acc_jerk pair-interactions/s fp64"

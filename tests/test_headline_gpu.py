@@ -112,3 +112,45 @@ def test_rectangular_65536_x_4194304():
     oracle.call_threaded(reference_lib(), "acc_jerk_kernel", "float64", CORES, *([len(sub)] + ia + [nj] + ja + ref))
     e = rel_err("acc_jerk_kernel", [g[sub] for g in got], ref)
     assert e <= 1e-12, e
+
+
+@pytest.mark.parametrize("shape", (0, 2))
+@pytest.mark.parametrize("eps2_case", ("zero", "positive", "mixed"))
+def test_grouped_kernel_mask_cases(shape, eps2_case):
+    """The grouped acc_jerk kernel folds e2_i into the r2 chain and tests the mask (the reference's
+    `r2 > 0`, acc_jerk_kernel_common.h:36) once per group of pairs, re-forming r2 only in groups where a
+    pair may be masked.  Every way into and around that rare branch, against the reference:
+    the pair of a particle with itself; coincident distinct particles with different velocities (masked
+    even when softened: their jerk term m (e2)^-3/2 v must NOT appear); pairs closer than 2^-10 softening
+    lengths (the branch is taken, the pair is NOT masked); and all of it with e2 = 0, e2 > 0 and mixed."""
+    n = 6 * 768 + 37                                 # whole and ragged i-blocks of both shapes
+    ps = ics.make_plummer(n, seed=13)
+    rng = np.random.default_rng(5)
+    eps = np.sqrt(2 * ps.eps2.max())                 # softening length of a pair
+    if eps2_case == "zero":
+        ps.eps2[...] = 0
+    elif eps2_case == "mixed":
+        ps.eps2[rng.random(n) < 0.5] = 0
+    dup = rng.choice(n // 2, 300, replace=False)     # coincident with a partner in the other half, own velocity
+    for a in ("rx", "ry", "rz"):
+        getattr(ps, a)[dup + n // 2] = getattr(ps, a)[dup]
+    near = np.setdiff1d(np.arange(n // 2), dup)[:300]  # a partner 1e-5 softening lengths away (not masked)
+    for a in ("rx", "ry", "rz"):
+        getattr(ps, a)[near + n // 2] = getattr(ps, a)[near] + 1e-5 * eps * rng.standard_normal(len(near))
+    data = as_dict(ps, "float64")
+    lib = cuda_lib("float64")
+    idx = np.unique(np.concatenate([dup, dup + n // 2, near, near + n // 2, rng.integers(0, n, 200)]))
+    ref = oracle_sample("acc_jerk_kernel", data, idx)
+    assert all(np.all(np.isfinite(r)) for r in ref)
+    for jg in (1, 3):
+        lib.tupan_cuda_force_plan(shape, 0, jg)
+        got = cuda_run("acc_jerk_kernel", "float64", data, data)
+        assert last_plan(lib) == (shape, 0, jg)
+        assert all(np.all(np.isfinite(g)) for g in got)
+        # per particle, not on the scale of the array: a jerk term that should have been masked is
+        # visible on the particle it belongs to
+        for lo in (0, 3):
+            g = np.stack([x[idx] for x in got[lo:lo + 3]])
+            r = np.stack(ref[lo:lo + 3])
+            err = np.sqrt(((g - r) ** 2).sum(0)) / np.sqrt((r ** 2).sum(0))
+            assert err.max() <= 1e-11, (shape, eps2_case, jg, lo, err.max(), idx[err.argmax()])

@@ -173,10 +173,11 @@ template <typename T> struct AccJerkOp {
     //   2   v' = v - alpha r for every pair, then per pair g = -(m q3) and the six accumulations,
     //       all with g as the LAST-defined multiplicand (ptxas puts the operand it shares between
     //       consecutive DFMAs in one slot when it is the later-defined one).
-    // Measured (profiles/r02_kernel_lab_grouped.txt, r02_kernel_lab3_w3.txt): W x U = 3 x 2 leaves 2.0
-    // uncached three-register DFMAs per pair (the first of each run of DFMAs that share an operand)
-    // instead of 9.3, and 5.8 instead of 6.9 non-FP64 instructions per pair: 71.4 clocks per pair in
-    // the lab kernel (round-1 kernel 75.1, 2 x 4 with one-trip loops 72.9).
+    // Measured (profiles/r02_kernel_lab_grouped.txt, r02_kernel_lab3_w3.txt, r02_kernel_lab3_fold.txt):
+    // W x U = 3 x 2 leaves 2.0 uncached three-register DFMAs per pair (the first of each run of DFMAs
+    // that share an operand) instead of 9.3, and 5.8 instead of 6.9 non-FP64 instructions per pair: 71.3
+    // clocks per pair in the lab kernel (round-1 kernel 75.1, 2 x 4 with one-trip loops 72.9); with e2_i
+    // folded into the r2 chain (31 FP64 instructions per pair, bit 4) 68.6 = 0.612 of the nominal peak.
 #ifndef TUPAN_AJ_GW
 #define TUPAN_AJ_GW 3
 #define TUPAN_AJ_GU 2
@@ -184,15 +185,17 @@ template <typename T> struct AccJerkOp {
 #endif
     // GMODE bit 0: block 1a on its own; bit 1: g formed in block 2 (see above); bit 2: block 2 pair by
     // pair; bit 3: the blocks are fenced by `if (one != 0)` instead of one-trip loops (two uniform
-    // branches per group instead of two loop headers with their counters)
-    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT, GMODE = 11 };
-    // second shape, 2 x 4 (512 instead of 768 particles per CTA; 72.9 clocks per pair): small and medium ni
-    enum { GALT = 1, GW2 = 2, GU2 = 4, GMODE2 = 11, GCOST2_PERMILLE = 1021 };
+    // branches per group instead of two loop headers with their counters); bit 4: e2_i folded into the
+    // r2 chain, the mask tested per group (group_phase1)
+    enum { GROUPED = (sizeof(T) == 8), GW = TUPAN_AJ_GW, GU = TUPAN_AJ_GU, GNT = TUPAN_AJ_GNT, GMODE = 27 };
+    // second shape, 2 x 4 (512 instead of 768 particles per CTA; 71.9 clocks per pair): small and medium ni
+    enum { GALT = 1, GW2 = 2, GU2 = 4, GMODE2 = 27, GCOST2_PERMILLE = 1047 };
     struct PV { T rx, ry, rz, vx, vy, vz, na, q3, mj; };
     template <int W, int U, int MODE>
     static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int one)
     {
         constexpr int G = W * U;
+        constexpr bool FOLD = (MODE & 16) != 0;      // e2_i rides in the r2 chain (one DADD per pair less)
         T r2[G], rv[G], e[G], y0[G];
 #pragma unroll
         for (int p = 0; p < G; ++p) {
@@ -200,12 +203,15 @@ template <typename T> struct AccJerkOp {
             const T(&rw)[NJP] = rows[p / W];
             o[p].rx = si[IX] - rw[JX]; o[p].ry = si[IY] - rw[JY]; o[p].rz = si[IZ] - rw[JZ];
             o[p].vx = si[IVX] - rw[J8_VX]; o[p].vy = si[IVY] - rw[J8_VY]; o[p].vz = si[IVZ] - rw[J8_VZ];
-            e[p] = si[IE] + rw[J8_E2];
+            e[p] = FOLD ? rw[J8_E2] : si[IE] + rw[J8_E2];
             o[p].mj = rw[JM];
         }
         auto chains = [&]() {
 #pragma unroll
-            for (int p = 0; p < G; ++p) { r2[p] = o[p].rx * o[p].rx; rv[p] = o[p].rx * o[p].vx; }
+            for (int p = 0; p < G; ++p) {
+                r2[p] = FOLD ? fma(o[p].rx, o[p].rx, s[p % W][IE]) : o[p].rx * o[p].rx;
+                rv[p] = o[p].rx * o[p].vx;
+            }
 #pragma unroll
             for (int p = 0; p < G; ++p) { r2[p] = fma(o[p].ry, o[p].ry, r2[p]); rv[p] = fma(o[p].ry, o[p].vy, rv[p]); }
 #pragma unroll
@@ -217,10 +223,34 @@ template <typename T> struct AccJerkOp {
 #pragma unroll 1
             for (int z = 0; z < ((MODE & 1) ? one : 1); ++z) chains();       // block 1a
         }
+        if (FOLD) {
+            // x = ((e2_i + rx^2) + ry^2 + rz^2) + e2_j: 31 FP64 instructions per pair.  The chain no longer
+            // holds the bare r2 the mask is read from (r2 zero or denormal: the pair of a particle with
+            // itself, coincident particles), so the group tests a NECESSARY condition -- the high word of
+            // the chain still equals that of e2_i: r2 < 2^-20 e2_i, or both zero -- with one chained
+            // compare per pair, and only a group with such a pair forms r2 again and zeroes the seeds of
+            // the pairs the mask really applies to (rsqrt_seed_masked's test).  A particle meets itself
+            // once per sweep, close pairs inside 1e-3 softening lengths are as rare.
+            bool cand = false;
 #pragma unroll
-        for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x = r2 + e2
+            for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
 #pragma unroll
-        for (int p = 0; p < G; ++p) y0[p] = rsqrt_seed_masked<false>(e[p], r2[p]);
+            for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x
+#pragma unroll
+            for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(e[p]));
+            if (cand) {
+#pragma unroll
+                for (int p = 0; p < G; ++p) {
+                    T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); q = fma(o[p].rz, o[p].rz, q);
+                    if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x = r2 + e2
+#pragma unroll
+            for (int p = 0; p < G; ++p) y0[p] = rsqrt_seed_masked<false>(e[p], r2[p]);
+        }
         T t[G], h[G];
 #pragma unroll
         for (int p = 0; p < G; ++p) t[p] = e[p] * y0[p];
