@@ -49,12 +49,12 @@ OUT6 = ("ax", "ay", "az", "jx", "jy", "jz")
 METRIC = "acc_jerk pair-interactions/s fp64"
 # dram__bytes_read.sum + dram__bytes_write.sum of the pair kernel, per launch, from ncu captures of
 # this command, keyed by (n, GPUs, j-chunks of the launch):
-#   round 2, grouped kernel, 32 chunks (profiles/r02_accjerk_grouped_n1m_dram.csv): 1.944 GB + 1.686 GB
+#   round 2, grouped 3x2 kernel, 17 chunks (profiles/r02_accjerk_grouped_n1m_dram.csv): 1.082 GB + 0.877 GB
 #   round 1, 25 chunks (profiles/r01_accjerk_v4_n1m_ncu_summary.txt): 1.568 GB + 1.358 GB
 # It exceeds the 184.5 MB of algorithmic bytes because the j range is split into chunks for wave
-# balance (each chunk writes a partial accumulator slot that finalize reads back); at 1.7 GB/s it is
-# 0.03 % of HBM bandwidth -- this kernel is FP64-pipe bound.
-NCU_TRAFFIC = {(1 << 20, 1, 32): 1944071168 + 1686260480, (1 << 20, 1, 25): 1567549000 + 1357939000}
+# balance (each chunk writes a partial accumulator slot that finalize reads back: 17 x 2^20 x 6 x 8 B =
+# 0.855 GB); at 1 GB/s it is 0.02 % of HBM bandwidth -- this kernel is FP64-pipe bound.
+NCU_TRAFFIC = {(1 << 20, 1, 17): 1082319872 + 877085440, (1 << 20, 1, 25): 1567549000 + 1357939000}
 KERNEL_NAME = "pair_kernel_grouped<AccJerkOp<double>>"
 PARITY_TOL = 1e-12           # BASELINE.json north_star: ~1e-12 in fp64 (summation order differs)
 PARITY_SAMPLE = 256          # i-particles per rank checked against the full j-set

@@ -92,6 +92,22 @@ def _loop_stats(ins):
     if best is None:
         return None
     body = ins[best[0]:best[1] + 1]
+    # rarely executed blocks: the range a per-thread predicated forward branch jumps over when that
+    # range holds no MUFU (the mask fix-up of a grouped kernel: `@!P0 BRA` over the block that re-forms
+    # r2).  The uniform fences (`BRA.U !UP0`) of the basic blocks are never taken and are not skipped.
+    skip = set()
+    end_addr = body[-1][0]
+    for addr, text in body:
+        m = re.match(r'^@!?P\d\s+BRA\s+(?:.*\s)?0x([0-9a-f]+)$', text)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if addr < tgt <= end_addr:
+            rng = [(a, t) for a, t in body if addr < a < tgt]
+            if rng and not any(operands(t)[0].startswith('MUFU') for _, t in rng):
+                skip.update(a for a, _ in rng)
+    rare = len(skip)
+    body = [(a, t) for a, t in body if a not in skip]
     mix = Counter()
     dp = 0
     clocks = 0.0
@@ -123,7 +139,7 @@ def _loop_stats(ins):
                 cur_reuse[slot] = reg_of(a)
         prev_reuse = cur_reuse
     other = sum(v for k, v in mix.items() if k not in ('DFMA', 'DADD', 'DMUL'))
-    return {"mix": mix, "dp": dp, "other": other, "three": three, "clocks": clocks, "n": len(body)}
+    return {"mix": mix, "dp": dp, "other": other, "three": three, "clocks": clocks, "n": len(body), "rare": rare}
 
 
 if __name__ == "__main__":

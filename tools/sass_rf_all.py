@@ -23,9 +23,10 @@ def main():
             continue
         tag = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
         tag = re.sub(r'\(.*', '', tag)
-        print("%-70s pairs/loop %5.1f  FP64/pair %5.2f  3-reg DFMA/pair %5.2f  other/pair %5.2f  model clk/pair %6.2f"
+        print("%-70s pairs/loop %5.1f  FP64/pair %5.2f  3-reg DFMA/pair %5.2f  other/pair %5.2f  model clk/pair %6.2f%s"
               % (tag[-70:], r["pairs"], r["dp"] / r["pairs"], r["three"] / r["pairs"], r["other"] / r["pairs"],
-                 r["clocks"] / r["pairs"]))
+                 r["clocks"] / r["pairs"],
+                 "  (+%d instructions in rarely taken blocks, not counted)" % r["rare"] if r.get("rare") else ""))
 
 
 if __name__ == "__main__":
