@@ -140,17 +140,19 @@ def test_grouped_kernel_mask_cases(shape, eps2_case):
     data = as_dict(ps, "float64")
     lib = cuda_lib("float64")
     idx = np.unique(np.concatenate([dup, dup + n // 2, near, near + n // 2, rng.integers(0, n, 200)]))
-    ref = oracle_sample("acc_jerk_kernel", data, idx)
-    assert all(np.all(np.isfinite(r)) for r in ref)
-    for jg in (1, 3):
-        lib.tupan_cuda_force_plan(shape, 0, jg)
-        got = cuda_run("acc_jerk_kernel", "float64", data, data)
-        assert last_plan(lib) == (shape, 0, jg)
-        assert all(np.all(np.isfinite(g)) for g in got)
-        # per particle, not on the scale of the array: a jerk term that should have been masked is
-        # visible on the particle it belongs to
-        for lo in (0, 3):
-            g = np.stack([x[idx] for x in got[lo:lo + 3]])
-            r = np.stack(ref[lo:lo + 3])
-            err = np.sqrt(((g - r) ** 2).sum(0)) / np.sqrt((r ** 2).sum(0))
-            assert err.max() <= 1e-11, (shape, eps2_case, jg, lo, err.max(), idx[err.argmax()])
+    # acc and phi run the same scheme in their grouped forms (AccOp / PhiOp::group_phase1)
+    for name in ("acc_jerk_kernel", "acc_kernel", "phi_kernel"):
+        ref = oracle_sample(name, data, idx)
+        assert all(np.all(np.isfinite(r)) for r in ref)
+        for jg in (1, 3):
+            lib.tupan_cuda_force_plan(shape, 0, jg)
+            got = cuda_run(name, "float64", data, data)
+            assert last_plan(lib) == (shape, 0, jg)
+            assert all(np.all(np.isfinite(g)) for g in got)
+            # per particle, not on the scale of the array: a jerk term that should have been masked is
+            # visible on the particle it belongs to
+            for lo in range(0, len(ref), 3):
+                g = np.stack([x[idx] for x in got[lo:lo + 3]])
+                r = np.stack(ref[lo:lo + 3])
+                err = np.sqrt(((g - r) ** 2).sum(0)) / np.sqrt((r ** 2).sum(0))
+                assert err.max() <= 1e-11, (name, shape, eps2_case, jg, lo, err.max(), idx[err.argmax()])

@@ -82,6 +82,68 @@ template <typename T> struct PhiOp {
     {
         out[0][i] = a[0];
     }
+
+    // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp / AccOp): 13 FP64 instructions per pair
+    // instead of 14 (e2_i in the r2 chain, the mask tested per group); the accumulations of the W pairs
+    // of a row share the row's mass and run back to back.
+    // Measured (profiles/r02_kernel_lab5_phi.txt, tools/kernel_lab5.cu): ungrouped 1072 Gpair/s (34.7 clocks per
+    // pair), 3 x 2 1200 (31.0; 110 registers, two CTAs per SM), 8 x 2 1192, 6 x 2 1130.
+#ifndef TUPAN_PHI_GROUPED
+#define TUPAN_PHI_GROUPED 1
+#define TUPAN_PHI_GW 3
+#define TUPAN_PHI_GU 2
+#endif
+    enum { GROUPED = (TUPAN_PHI_GROUPED != 0 && sizeof(T) == 8), GW = TUPAN_PHI_GW, GU = TUPAN_PHI_GU, GNT = 256,
+           GMODE = 8, GALT = 0 };
+    struct PV { T r1, m; };
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int)
+    {
+        constexpr int G = W * U;
+        T rx[G], ry[G], rz[G], r2[G], x[G], y0[G], t[G], h[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            const T(&si)[NI] = s[p % W];
+            const T(&rw)[NJP] = rows[p / W];
+            rx[p] = si[IX] - rw[JX]; ry[p] = si[IY] - rw[JY]; rz[p] = si[IZ] - rw[JZ];
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(rx[p], rx[p], s[p % W][IE]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(ry[p], ry[p], r2[p]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(rz[p], rz[p], r2[p]);
+        bool cand = false;
+#pragma unroll
+        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
+#pragma unroll
+        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J5_E2];
+#pragma unroll
+        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
+        if (cand) {
+#pragma unroll
+            for (int p = 0; p < G; ++p) {
+                T q = rx[p] * rx[p]; q = fma(ry[p], ry[p], q); q = fma(rz[p], rz[p], q);
+                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) { o[p].r1 = y0[p] * t[p]; o[p].m = rows[p / W][JM]; }
+    }
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
+    {
+#pragma unroll
+        for (int p = 0; p < W * U; ++p) a[p % W][0] = fma(-o[p].m, o[p].r1, a[p % W][0]);   // p / W = row: m shared
+    }
 };
 
 // =======================================================================================
@@ -112,6 +174,81 @@ template <typename T> struct AccOp {
     static TUPAN_DEV void finish(const T* const*, long long i, const T (&a)[NA], const Params&, T* const* out)
     {
         out[0][i] = a[0]; out[1][i] = a[1]; out[2][i] = a[2];
+    }
+
+    // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp for the why): G = W x U pairs operation
+    // by operation, 18 FP64 instructions per pair instead of 19 -- e2_i rides in the r2 chain and the mask
+    // (r2 zero or denormal) is tested once per group through a necessary condition, as in
+    // AccJerkOp::group_phase1 -- and the three accumulations of a pair, which share g, in a block of
+    // their own.
+    // Measured (profiles/r02_kernel_lab4_acc.txt, tools/kernel_lab4.cu): ungrouped 779.7 Gpair/s (47.7 clocks
+    // per pair), 6 x 2 902.5 (41.3; 238 registers, 1536 particles per CTA), 3 x 2 873.3 (42.6; 768 per CTA:
+    // the second shape, for small ni).
+#ifndef TUPAN_ACC_GROUPED
+#define TUPAN_ACC_GROUPED 1
+#define TUPAN_ACC_GW 6
+#define TUPAN_ACC_GU 2
+#endif
+    enum { GROUPED = (TUPAN_ACC_GROUPED != 0 && sizeof(T) == 8), GW = TUPAN_ACC_GW, GU = TUPAN_ACC_GU, GNT = 256,
+           GMODE = 8 };
+    enum { GALT = 1, GW2 = 3, GU2 = 2, GMODE2 = 8, GCOST2_PERMILLE = 1033 };
+    struct PV { T rx, ry, rz, g; };
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int)
+    {
+        constexpr int G = W * U;
+        T r2[G], x[G], y0[G], t[G], h[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            const T(&si)[NI] = s[p % W];
+            const T(&rw)[NJP] = rows[p / W];
+            o[p].rx = si[IX] - rw[JX]; o[p].ry = si[IY] - rw[JY]; o[p].rz = si[IZ] - rw[JZ];
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(o[p].rx, o[p].rx, s[p % W][IE]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(o[p].ry, o[p].ry, r2[p]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(o[p].rz, o[p].rz, r2[p]);
+        bool cand = false;
+#pragma unroll
+        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
+#pragma unroll
+        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J5_E2];
+#pragma unroll
+        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
+        if (cand) {
+#pragma unroll
+            for (int p = 0; p < G; ++p) {
+                T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); q = fma(o[p].rz, o[p].rz, q);
+                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = y0[p] * t[p];                 // 1/sqrt(x)
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = h[p] * t[p];                  // x^-3/2
+#pragma unroll
+        for (int p = 0; p < G; ++p) o[p].g = -(rows[p / W][JM] * h[p]);
+    }
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
+    {
+#pragma unroll
+        for (int p = 0; p < W * U; ++p) {
+            T(&ac)[NA] = a[p % W];
+            ac[0] = fma(o[p].rx, o[p].g, ac[0]); ac[1] = fma(o[p].ry, o[p].g, ac[1]); ac[2] = fma(o[p].rz, o[p].g, ac[2]);
+        }
     }
 };
 
