@@ -140,8 +140,8 @@ def test_grouped_kernel_mask_cases(shape, eps2_case):
     data = as_dict(ps, "float64")
     lib = cuda_lib("float64")
     idx = np.unique(np.concatenate([dup, dup + n // 2, near, near + n // 2, rng.integers(0, n, 200)]))
-    # acc and phi run the same scheme in their grouped forms (AccOp / PhiOp::group_phase1)
-    for name in ("acc_jerk_kernel", "acc_kernel", "phi_kernel"):
+    # acc, phi, tstep and nreg_X run the same scheme in their grouped forms (their Op's group_phase1)
+    for name in ("acc_jerk_kernel", "acc_kernel", "phi_kernel", "tstep_kernel", "nreg_Xkernel"):
         ref = oracle_sample(name, data, idx)
         assert all(np.all(np.isfinite(r)) for r in ref)
         for jg in (1, 3):

@@ -32,7 +32,7 @@ def test_every_kernel_gets_a_valid_plan(prec):
             if split != 1:
                 assert js == 0
             if split == 2:                       # only kernels with a second group shape may be given it
-                assert kernel in ("acc_jerk_kernel", "acc_kernel") and prec == "float64"
+                assert kernel in ("acc_jerk_kernel", "acc_kernel", "tstep_kernel", "nreg_Xkernel") and prec == "float64"
 
 
 def test_acc_jerk_fp64_shapes_follow_the_measurements():

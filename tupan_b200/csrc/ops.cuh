@@ -684,6 +684,102 @@ template <typename T> struct TstepOp {
         out[0][i] = p.eta * rsqrt_full(T(1) + a[0]);
         out[1][i] = p.eta * rsqrt_full(T(1) + a[1]);
     }
+
+    // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp): 36 FP64 instructions per pair instead
+    // of 37 (e2_i in the r2 chain, the r2 mask tested per group); the r2 and r.v chains step by step in a
+    // block of their own -- fma(ry, ry, r2) next to fma(ry, vy, rv), which finds ry in the operand-reuse
+    // cache.  The second seed keeps its per-pair mask (w2's own exponent).
+    // Measured (profiles/r02_kernel_lab6_tstep.txt, tools/kernel_lab6.cu): ungrouped 394.8 Gpair/s (94.3 clocks
+    // per pair), 3 x 2 429.2 (86.7), 4 x 2 427.1, 2 x 2 406.2 (the second shape, 512 particles per CTA).
+#ifndef TUPAN_TSTEP_GROUPED
+#define TUPAN_TSTEP_GROUPED 1
+#define TUPAN_TSTEP_GW 3
+#define TUPAN_TSTEP_GU 2
+#endif
+    enum { GROUPED = (TUPAN_TSTEP_GROUPED != 0 && sizeof(T) == 8), GW = TUPAN_TSTEP_GW, GU = TUPAN_TSTEP_GU, GNT = 256,
+           GMODE = 8 };
+    enum { GALT = 1, GW2 = 2, GU2 = 2, GMODE2 = 8, GCOST2_PERMILLE = 1056 };
+    struct PV { T w2; };
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params& prm, int one)
+    {
+        constexpr int G = W * U;
+        T rx[G], ry[G], rz[G], vx[G], vy[G], vz[G], m2[G], r2[G], rv[G], v2[G], x[G], y0[G], t[G], h[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            const T(&si)[NI] = s[p % W];
+            const T(&rw)[NJP] = rows[p / W];
+            rx[p] = si[IX] - rw[JX]; ry[p] = si[IY] - rw[JY]; rz[p] = si[IZ] - rw[JZ];
+            vx[p] = si[IVX] - rw[J8_VX]; vy[p] = si[IVY] - rw[J8_VY]; vz[p] = si[IVZ] - rw[J8_VZ];
+            m2[p] = si[IM] + rw[JM];
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) v2[p] = vx[p] * vx[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) v2[p] = fma(vy[p], vy[p], v2[p]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) v2[p] = fma(vz[p], vz[p], v2[p]);
+        if (one != 0) {                 // the r2 and r.v chains, fenced (AccJerkOp's block 1a)
+#pragma unroll
+            for (int p = 0; p < G; ++p) { r2[p] = fma(rx[p], rx[p], s[p % W][IE]); rv[p] = rx[p] * vx[p]; }
+#pragma unroll
+            for (int p = 0; p < G; ++p) { r2[p] = fma(ry[p], ry[p], r2[p]); rv[p] = fma(ry[p], vy[p], rv[p]); }
+#pragma unroll
+            for (int p = 0; p < G; ++p) { r2[p] = fma(rz[p], rz[p], r2[p]); rv[p] = fma(rz[p], vz[p], rv[p]); }
+        }
+        bool cand = false;
+#pragma unroll
+        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
+#pragma unroll
+        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J8_E2];
+#pragma unroll
+        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
+        if (cand) {
+#pragma unroll
+            for (int p = 0; p < G; ++p) {
+                T q = rx[p] * rx[p]; q = fma(ry[p], ry[p], q); q = fma(rz[p], rz[p], q);
+                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = y0[p] * t[p];                 // 1/r
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];                  // 1/r^2
+        // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv   (pair())
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = m2[p] * t[p];                 // phi2
+#pragma unroll
+        for (int p = 0; p < G; ++p) v2[p] = v2[p] + t[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) v2[p] = h[p] * v2[p];                // w2
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], v2[p]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = h[p] * t[p];                  // gamma without the eta/sqrt(w2)
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = rsqrt_scaled<false>(v2[p], v2[p], prm.eta, prm.eta_k1, prm.eta_k2);
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = t[p] * h[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) o[p].w2 = fma(-t[p], rv[p], v2[p]);
+    }
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
+    {
+#pragma unroll
+        for (int p = 0; p < W * U; ++p) {
+            a[p % W][0] += o[p].w2;
+            a[p % W][1] = rmax_nonneg(a[p % W][1], o[p].w2);
+        }
+    }
 };
 
 // =======================================================================================
@@ -724,6 +820,90 @@ template <typename T> struct NregXOp {
 #pragma unroll
         for (int k = 0; k < 6; ++k) out[k][i] = a[k];
         out[6][i] = ia[0][i] * a[6];
+    }
+
+    // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp): 28 FP64 instructions per pair instead
+    // of 29 (e2_i in the r2 chain, the mask tested per group); the four accumulations that share the row's
+    // mass run back to back for the W pairs of a row, then the three that share g for each pair.
+    // Measured (profiles/r02_kernel_lab7_nregx.txt, tools/kernel_lab7.cu): ungrouped 538.2 Gpair/s (69.2 clocks
+    // per pair), 4 x 2 583.0 (63.9), 3 x 2 568.8, 2 x 2 572.1 (the second shape, 512 particles per CTA).
+#ifndef TUPAN_NREGX_GROUPED
+#define TUPAN_NREGX_GROUPED 1
+#define TUPAN_NREGX_GW 4
+#define TUPAN_NREGX_GU 2
+#endif
+    enum { GROUPED = (TUPAN_NREGX_GROUPED != 0 && sizeof(T) == 8), GW = TUPAN_NREGX_GW, GU = TUPAN_NREGX_GU, GNT = 256,
+           GMODE = 8 };
+    enum { GALT = 1, GW2 = 2, GU2 = 2, GMODE2 = 8, GCOST2_PERMILLE = 1019 };
+    struct PV { T rx, ry, rz, r1, g, m; };
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params& prm, int)
+    {
+        constexpr int G = W * U;
+        T r2[G], x[G], y0[G], t[G], h[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            const T(&si)[NI] = s[p % W];
+            const T(&rw)[NJP] = rows[p / W];
+            o[p].rx = si[IX] - rw[JX]; o[p].ry = si[IY] - rw[JY]; o[p].rz = si[IZ] - rw[JZ];
+            t[p] = si[IVX] - rw[J8_VX]; h[p] = si[IVY] - rw[J8_VY]; x[p] = si[IVZ] - rw[J8_VZ];
+            o[p].m = rw[JM];
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            o[p].rx = fma(t[p], prm.dt, o[p].rx); o[p].ry = fma(h[p], prm.dt, o[p].ry); o[p].rz = fma(x[p], prm.dt, o[p].rz);
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(o[p].rx, o[p].rx, s[p % W][IE]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(o[p].ry, o[p].ry, r2[p]);
+#pragma unroll
+        for (int p = 0; p < G; ++p) r2[p] = fma(o[p].rz, o[p].rz, r2[p]);
+        bool cand = false;
+#pragma unroll
+        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
+#pragma unroll
+        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J8_E2];
+#pragma unroll
+        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
+        if (cand) {
+#pragma unroll
+            for (int p = 0; p < G; ++p) {
+                T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); q = fma(o[p].rz, o[p].rz, q);
+                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
+#pragma unroll
+        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
+#pragma unroll
+        for (int p = 0; p < G; ++p) o[p].r1 = y0[p] * t[p];
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = o[p].r1 * o[p].r1;
+#pragma unroll
+        for (int p = 0; p < G; ++p) h[p] = h[p] * o[p].r1;
+#pragma unroll
+        for (int p = 0; p < G; ++p) o[p].g = -(o[p].m * h[p]);
+    }
+    template <int W, int U, int MODE>
+    static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
+    {
+#pragma unroll
+        for (int p = 0; p < W * U; ++p) {             // p / W = row: m shared by 4 W consecutive DFMAs
+            T(&ac)[NA] = a[p % W];
+            ac[0] = fma(o[p].rx, o[p].m, ac[0]); ac[1] = fma(o[p].ry, o[p].m, ac[1]); ac[2] = fma(o[p].rz, o[p].m, ac[2]);
+            ac[6] = fma(o[p].r1, o[p].m, ac[6]);
+        }
+#pragma unroll
+        for (int p = 0; p < W * U; ++p) {
+            T(&ac)[NA] = a[p % W];
+            ac[3] = fma(o[p].rx, o[p].g, ac[3]); ac[4] = fma(o[p].ry, o[p].g, ac[4]); ac[5] = fma(o[p].rz, o[p].g, ac[5]);
+        }
     }
 };
 
