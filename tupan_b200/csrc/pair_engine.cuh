@@ -304,16 +304,18 @@ __global__ void __launch_bounds__(NT) pair_kernel(const __grid_constant__ PairAr
 // basic block, interleaves them with everything else and leaves 9 of them uncached: 64 + 9 clocks
 // per pair modelled, 74.4 measured.  Here the G = W x U pairs of a group of U rows are written
 // operation by operation (dependent operations are G instructions apart), and the operand-sharing
-// DFMAs live in basic blocks of their own: a loop whose trip count is a kernel argument (always 1)
-// keeps ptxas from merging the blocks, and inside such a block it groups the DFMAs by shared
-// operand and flags the reuse itself: 3.2 uncached three-register DFMAs per pair instead of 9.
+// DFMAs live in basic blocks of their own: a branch on a kernel argument that is always 1
+// (PairArgs::one; `if (one != 0)`, GMODE bit 3, or a loop with that trip count) keeps ptxas from
+// merging the blocks, and inside such a block it groups the DFMAs by shared operand and flags the
+// reuse itself: 2.0 (3 x 2 pairs) to 3.2 (2 x 4) uncached three-register DFMAs per pair instead of 9.
 //
 // An Op opts in with
-//   enum { GROUPED = 1, GW, GU, GNT };   particles per thread, rows per group, threads per CTA
+//   enum { GROUPED = 1, GW, GU, GNT, GMODE };  particles per thread, rows per group, threads per CTA,
+//                                          mode bits handed to the phases (bit 3 is read here too)
+//   enum { GALT, GW2, GU2, GMODE2, GCOST2_PERMILLE };   optional second shape (GroupedAlt below)
 //   struct PV;                             what phase 1 hands to phase 2 for one pair
-//   group_phase1<W, U>(is, rows, pv, prm, one)   everything up to the accumulation, W x U pairs
-//   group_phase2<W, U>(pv, acc, prm)       the accumulation DFMAs of the group (run inside the
-//                                          kernel's one-trip loop)
+//   group_phase1<W, U, MODE>(is, rows, pv, prm, one)   everything up to the accumulation, W x U pairs
+//   group_phase2<W, U, MODE>(pv, acc, prm)  the accumulation DFMAs of the group (fenced by the kernel)
 // Partial tiles (the end of a j range) take Op::pair row by row.
 // ---------------------------------------------------------------------------------------
 template <class Op, typename = void> struct Grouped { enum { value = 0, W = 1, U = 1, NT = 256, MODE = 0 }; };
