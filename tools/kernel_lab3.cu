@@ -1,7 +1,12 @@
-// kernel_lab3.cu -- round 2: shapes of the PRODUCTION grouped acc_jerk kernel (pair_kernel_grouped,
-// pair_engine.cuh) next to the round-1 kernel, timed at whole waves through the production launcher.
+// kernel_lab3.cu -- round 2: group shapes (W particles per thread x U rows, threads per CTA, GMODE bits) of a
+// PRODUCTION grouped kernel (pair_kernel_grouped, pair_engine.cuh) next to its plain kernel (W = 0), timed
+// at whole waves through the production kernel templates.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DTUPAN_FP64 \
+//        [-DLAB_OP=1..4] [-DLAB_LIST_FILE='"list.h"'] [-Xptxas -regUsageLevel -Xptxas 10] \
 //        -o tools/bin/kernel_lab3 tools/kernel_lab3.cu
+// LAB_OP: 0 acc_jerk (default; profiles/r02_kernel_lab3_*.txt), 1 acc (r02_kernel_lab4_acc.txt), 2 phi
+// (r02_kernel_lab5_phi.txt), 3 tstep (r02_kernel_lab6_tstep.txt), 4 nreg_X (r02_kernel_lab7_nregx.txt).
+// LAB_LIST_FILE defines LAB_LIST as a sequence of X(W, U, NT, MODE).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -11,16 +16,48 @@
 
 using namespace tupan;
 
+#ifndef LAB_OP
+#define LAB_OP 0
+#endif
+#if LAB_OP == 0
+typedef AccJerkOp<double> LabOp;
+enum { LAB_NIN = 8, LAB_NOUT = 6, LAB_FLOPS = 42 };
+static void lab_params(NoParams&) {}
+#define LAB_DEFAULT X(0, 8, 256, 0) X(3, 2, 256, 27) X(3, 2, 256, 11) X(2, 4, 256, 27) X(2, 4, 256, 11) X(2, 4, 256, 3)
+#elif LAB_OP == 1
+typedef AccOp<double> LabOp;
+enum { LAB_NIN = 5, LAB_NOUT = 3, LAB_FLOPS = 20 };
+static void lab_params(NoParams&) {}
+#define LAB_DEFAULT X(0, 4, 256, 0) X(4, 2, 256, 8) X(3, 2, 256, 8) X(2, 4, 256, 8) X(3, 4, 256, 8) X(4, 4, 256, 8) \
+    X(6, 2, 256, 8) X(8, 1, 256, 8) X(6, 1, 256, 8) X(4, 2, 256, 0)
+#elif LAB_OP == 2
+typedef PhiOp<double> LabOp;
+enum { LAB_NIN = 5, LAB_NOUT = 1, LAB_FLOPS = 14 };
+static void lab_params(NoParams&) {}
+#define LAB_DEFAULT X(0, 4, 256, 0) X(4, 2, 256, 8) X(3, 2, 256, 8) X(6, 2, 256, 8) X(8, 2, 256, 8) X(4, 4, 256, 8) \
+    X(8, 1, 256, 8) X(6, 2, 256, 0) X(3, 4, 256, 8)
+#elif LAB_OP == 3
+typedef TstepOp<double> LabOp;
+enum { LAB_NIN = 8, LAB_NOUT = 2, LAB_FLOPS = 42 };
+static void lab_params(TstepParams<double>& p) { p.eta = 1.0 / 64; p.eta_k1 = p.eta * 0.5; p.eta_k2 = p.eta * 0.375; }
+#define LAB_DEFAULT X(0, 4, 256, 0) X(3, 2, 256, 8) X(2, 2, 256, 8) X(2, 4, 256, 8) X(4, 2, 256, 8) X(4, 1, 256, 8) X(3, 1, 256, 8)
+#else
+typedef NregXOp<double> LabOp;
+enum { LAB_NIN = 8, LAB_NOUT = 7, LAB_FLOPS = 37 };
+static void lab_params(DtParams<double>& p) { p.dt = 1.0 / 64; }
+#define LAB_DEFAULT X(0, 4, 256, 0) X(3, 2, 256, 8) X(2, 2, 256, 8) X(2, 4, 256, 8) X(4, 2, 256, 8) X(4, 1, 256, 8) X(3, 1, 256, 8)
+#endif
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
 // the production Op with another group shape; W = 0: the round-1 kernel (not grouped)
-template <int W, int U, int NT_, int MODE_> struct AJ : AccJerkOp<double> {
+template <int W, int U, int NT_, int MODE_> struct AJ : LabOp {
     enum { GROUPED = W > 0, GW = W > 0 ? W : 1, GU = U, GNT = NT_, GMODE = MODE_ };
 };
 
 template <class Op>
 static double run_variant(const char* name, const InRefs<double>& in, long long n_alloc, const double* jpack,
-                          long long nj, double* out[6], int sms, bool self)
+                          long long nj, double* out[LAB_NOUT], int sms, bool self)
 {
     typedef Tune<Op> U;
     auto k = KernelOf<Op, false>::template get<U::NT, U::TJ, U::STAGES, false>();
@@ -41,8 +78,8 @@ static double run_variant(const char* name, const InRefs<double>& in, long long 
     const long long ioff = self ? 0 : nj;
     for (int q = 0; q < MAX_IN; ++q) a.i.p[q] = in.p[q] ? in.p[q] + ioff : nullptr;
     a.ni = ni; a.jpack = jpack; a.seg.nseg = 0; a.j0 = 0; a.j1 = nj; a.jchunk = nj; a.js_log2 = 0; a.slot0 = 0;
-    a.partial = nullptr; a.one = 1;
-    for (int q = 0; q < MAX_OUT; ++q) a.out.p[q] = q < 6 ? out[q] : nullptr;
+    a.partial = nullptr; a.one = 1; lab_params(a.prm);
+    for (int q = 0; q < MAX_OUT; ++q) a.out.p[q] = q < LAB_NOUT ? out[q] : nullptr;
     dim3 grid((unsigned)(ni / IB), 1);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -61,14 +98,14 @@ static double run_variant(const char* name, const InRefs<double>& in, long long 
     }
     std::vector<double> h(1024);
     double cs = 0;
-    for (int q = 0; q < 6; ++q) {
+    for (int q = 0; q < LAB_NOUT; ++q) {
         CK(cudaMemcpy(h.data(), out[q], 1024 * sizeof(double), cudaMemcpyDeviceToHost));
         for (int i = 0; i < 1024; ++i) cs += fabs(h[i]);
     }
     const double gp = (double)ni * nj / (best * 1e-3) * 1e-9;
     printf("%-30s %s regs=%3d occ=%d smem=%6zu ni=%7lld %8.3f ms %7.1f Gpair/s %5.2f clk/pair  frac %.4f  cs %.12e\n",
            name, self ? "self" : "rect", fa.numRegs, occ, smem, ni, best, gp, 148.0 * 4 * 32 * 1.965e9 / (gp * 1e9),
-           gp * 42e9 / (148.0 * 128 * 1.965e9), cs);
+           gp * (LAB_FLOPS * 1e9) / (148.0 * 128 * 1.965e9), cs);
     return gp;
 }
 
@@ -76,9 +113,7 @@ static double run_variant(const char* name, const InRefs<double>& in, long long 
 #include LAB_LIST_FILE
 #endif
 #ifndef LAB_LIST
-#define LAB_LIST \
-    X(0, 8, 256, 0) X(2, 4, 256, 4) X(2, 4, 256, 7) X(2, 4, 256, 3) X(2, 4, 256, 1) X(2, 4, 256, 0) \
-    X(3, 2, 256, 4) X(3, 2, 256, 5) X(3, 2, 256, 7) X(3, 2, 256, 3)
+#define LAB_LIST LAB_DEFAULT
 #endif
 
 int main(int argc, char** argv)
@@ -100,13 +135,13 @@ int main(int argc, char** argv)
     CK(cudaMalloc(&d, 8 * n * sizeof(double)));
     CK(cudaMemcpy(d, h.data(), 8 * n * sizeof(double), cudaMemcpyHostToDevice));
     InRefs<double> in;
-    for (int k = 0; k < MAX_IN; ++k) in.p[k] = k < 8 ? d + k * n : nullptr;
+    for (int k = 0; k < MAX_IN; ++k) in.p[k] = k < LAB_NIN ? d + k * n : nullptr;
     double* jpack;
     CK(cudaMalloc(&jpack, nj * 8 * sizeof(double)));
-    pack_j_kernel<AccJerkOp<double>><<<296, 256>>>(in, nj, jpack);
+    pack_j_kernel<LabOp><<<296, 256>>>(in, nj, jpack);
     CK(cudaDeviceSynchronize());
-    double* out[6];
-    for (int q = 0; q < 6; ++q) CK(cudaMalloc(&out[q], n * sizeof(double)));
+    double* out[LAB_NOUT];
+    for (int q = 0; q < LAB_NOUT; ++q) CK(cudaMalloc(&out[q], n * sizeof(double)));
     printf("%s, %d SMs, nj = %lld\n", p.name, sms, nj);
 #define X(W, U_, NT_, D) run_variant<AJ<W, U_, NT_, D>>("W" #W " U" #U_ " NT" #NT_ " mode" #D, in, n - nj, jpack, nj, out, sms, true);
     LAB_LIST

@@ -86,7 +86,7 @@ template <typename T> struct PhiOp {
     // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp / AccOp): 13 FP64 instructions per pair
     // instead of 14 (e2_i in the r2 chain, the mask tested per group); the accumulations of the W pairs
     // of a row share the row's mass and run back to back.
-    // Measured (profiles/r02_kernel_lab5_phi.txt, tools/kernel_lab5.cu): ungrouped 1072 Gpair/s (34.7 clocks per
+    // Measured (profiles/r02_kernel_lab5_phi.txt, tools/kernel_lab3.cu -DLAB_OP=2): ungrouped 1072 Gpair/s (34.7 clocks per
     // pair), 3 x 2 1200 (31.0; 110 registers, two CTAs per SM), 8 x 2 1192, 6 x 2 1130.
 #ifndef TUPAN_PHI_GROUPED
 #define TUPAN_PHI_GROUPED 1
@@ -181,7 +181,7 @@ template <typename T> struct AccOp {
     // (r2 zero or denormal) is tested once per group through a necessary condition, as in
     // AccJerkOp::group_phase1 -- and the three accumulations of a pair, which share g, in a block of
     // their own.
-    // Measured (profiles/r02_kernel_lab4_acc.txt, tools/kernel_lab4.cu): ungrouped 779.7 Gpair/s (47.7 clocks
+    // Measured (profiles/r02_kernel_lab4_acc.txt, tools/kernel_lab3.cu -DLAB_OP=1): ungrouped 779.7 Gpair/s (47.7 clocks
     // per pair), 6 x 2 902.5 (41.3; 238 registers, 1536 particles per CTA), 3 x 2 873.3 (42.6; 768 per CTA:
     // the second shape, for small ni).
 #ifndef TUPAN_ACC_GROUPED
@@ -689,7 +689,7 @@ template <typename T> struct TstepOp {
     // of 37 (e2_i in the r2 chain, the r2 mask tested per group); the r2 and r.v chains step by step in a
     // block of their own -- fma(ry, ry, r2) next to fma(ry, vy, rv), which finds ry in the operand-reuse
     // cache.  The second seed keeps its per-pair mask (w2's own exponent).
-    // Measured (profiles/r02_kernel_lab6_tstep.txt, tools/kernel_lab6.cu): ungrouped 394.8 Gpair/s (94.3 clocks
+    // Measured (profiles/r02_kernel_lab6_tstep.txt, tools/kernel_lab3.cu -DLAB_OP=3): ungrouped 394.8 Gpair/s (94.3 clocks
     // per pair), 3 x 2 429.2 (86.7), 4 x 2 427.1, 2 x 2 406.2 (the second shape, 512 particles per CTA).
 #ifndef TUPAN_TSTEP_GROUPED
 #define TUPAN_TSTEP_GROUPED 1
@@ -825,7 +825,7 @@ template <typename T> struct NregXOp {
     // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp): 28 FP64 instructions per pair instead
     // of 29 (e2_i in the r2 chain, the mask tested per group); the four accumulations that share the row's
     // mass run back to back for the W pairs of a row, then the three that share g for each pair.
-    // Measured (profiles/r02_kernel_lab7_nregx.txt, tools/kernel_lab7.cu): ungrouped 538.2 Gpair/s (69.2 clocks
+    // Measured (profiles/r02_kernel_lab7_nregx.txt, tools/kernel_lab3.cu -DLAB_OP=4): ungrouped 538.2 Gpair/s (69.2 clocks
     // per pair), 4 x 2 583.0 (63.9), 3 x 2 568.8, 2 x 2 572.1 (the second shape, 512 particles per CTA).
 #ifndef TUPAN_NREGX_GROUPED
 #define TUPAN_NREGX_GROUPED 1
