@@ -132,6 +132,60 @@ TUPAN_DEV float rsqrt_scaled(float x, float r2, float k0, float k1, float)
 #endif
 }
 
+// ---------------------------------------------------------------------------------------
+// The same seed and step for the G pairs of a group (pair_kernel_grouped), written operation by
+// operation, with the softening of the i-particle FOLDED into the r2 chain:
+//     c = fma(rz, rz, fma(ry, ry, fma(rx, rx, e2_i))),   x = c + e2_j
+// is one FP64 instruction per pair less than r2 + (e2_i + e2_j).  The chain c no longer holds the
+// bare r2 the reference's mask reads (`r2 > 0`, e.g. acc_jerk_kernel_common.h:36 -- it applies to
+// coincident particles even when they are softened), so the group tests a NECESSARY condition for
+// a masked pair instead -- the high word of c still equals the high word of e2_i, i.e.
+// r2 < 2^-20 e2_i or both zero -- with one predicate-chained ISETP per pair, and only a group that
+// has such a pair forms r2 again (bare_r2(p)) and zeroes the seeds the mask really applies to, by
+// rsqrt_seed_masked's criterion (r2 zero or denormal).  A particle meets itself once per sweep;
+// pairs inside 1e-3 softening lengths are as rare.  The seed's low word is zero (CLEAN).
+//   c[p]      the chain;  ei_hi(p)  high word of the pair's e2_i;  ej(p)  the pair's e2_j
+//   x[p], y0[p]  out: softened r2 and the (masked) rsqrt seed
+// tests/test_headline_gpu.py::test_grouped_kernel_mask_cases drives every way through the branch.
+// ---------------------------------------------------------------------------------------
+template <int G, class EI, class EJ, class R2>
+TUPAN_DEV void group_fold_seeds(const double (&c)[G], EI ei_hi, EJ ej, R2 bare_r2, double (&x)[G], double (&y0)[G])
+{
+    bool cand = false;
+#pragma unroll
+    for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(c[p]) == ei_hi(p));
+#pragma unroll
+    for (int p = 0; p < G; ++p) x[p] = c[p] + ej(p);
+#pragma unroll
+    for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
+    if (cand) {
+#pragma unroll
+        for (int p = 0; p < G; ++p) {
+            const double q = bare_r2(p);
+            if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = 0.0;
+        }
+    }
+}
+template <int G, class EI, class EJ, class R2>
+TUPAN_DEV void group_fold_seeds(const float (&)[G], EI, EJ, R2, float (&)[G], float (&)[G]) {}   // fp64 only
+
+// y[p] = k / sqrt(x[p]) from the seeds: the cubic step of rsqrt_scaled, operation by operation.
+template <int G, typename T>
+TUPAN_DEV void group_rsqrt_step(const T (&x)[G], const T (&y0)[G], T k0, T k1, T k2, T (&y)[G])
+{
+    T t[G], h[G];
+#pragma unroll
+    for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
+#pragma unroll
+    for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
+#pragma unroll
+    for (int p = 0; p < G; ++p) t[p] = fma(h[p], k2, k1);
+#pragma unroll
+    for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], k0);
+#pragma unroll
+    for (int p = 0; p < G; ++p) y[p] = y0[p] * t[p];
+}
+
 template <typename T> struct InvR { T r1, r2, r3; };
 
 // x = r2 + e2 (softened).  Returns 1/r, 1/r^2, 1/r^3 of the softened distance, all 0 when the

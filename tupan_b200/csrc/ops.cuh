@@ -100,7 +100,7 @@ template <typename T> struct PhiOp {
     static TUPAN_DEV void group_phase1(const T (*s)[NI], const T (*rows)[NJP], PV (&o)[W * U], const Params&, int)
     {
         constexpr int G = W * U;
-        T rx[G], ry[G], rz[G], r2[G], x[G], y0[G], t[G], h[G];
+        T rx[G], ry[G], rz[G], r2[G], x[G], y0[G], t[G];
 #pragma unroll
         for (int p = 0; p < G; ++p) {
             const T(&si)[NI] = s[p % W];
@@ -113,30 +113,11 @@ template <typename T> struct PhiOp {
         for (int p = 0; p < G; ++p) r2[p] = fma(ry[p], ry[p], r2[p]);
 #pragma unroll
         for (int p = 0; p < G; ++p) r2[p] = fma(rz[p], rz[p], r2[p]);
-        bool cand = false;
+        group_fold_seeds<G>(r2, [&](int p) { return __double2hiint(s[p % W][IE]); }, [&](int p) { return rows[p / W][J5_E2]; },
+                            [&](int p) { T q = rx[p] * rx[p]; q = fma(ry[p], ry[p], q); return fma(rz[p], rz[p], q); }, x, y0);
+        group_rsqrt_step<G>(x, y0, T(1), T(0.5), T(0.375), t);
 #pragma unroll
-        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
-#pragma unroll
-        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J5_E2];
-#pragma unroll
-        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
-        if (cand) {
-#pragma unroll
-            for (int p = 0; p < G; ++p) {
-                T q = rx[p] * rx[p]; q = fma(ry[p], ry[p], q); q = fma(rz[p], rz[p], q);
-                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
-#pragma unroll
-        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) { o[p].r1 = y0[p] * t[p]; o[p].m = rows[p / W][JM]; }
+        for (int p = 0; p < G; ++p) { o[p].r1 = t[p]; o[p].m = rows[p / W][JM]; }
     }
     template <int W, int U, int MODE>
     static TUPAN_DEV void group_phase2(PV (&o)[W * U], T (*a)[NA], const Params&)
@@ -210,30 +191,10 @@ template <typename T> struct AccOp {
         for (int p = 0; p < G; ++p) r2[p] = fma(o[p].ry, o[p].ry, r2[p]);
 #pragma unroll
         for (int p = 0; p < G; ++p) r2[p] = fma(o[p].rz, o[p].rz, r2[p]);
-        bool cand = false;
-#pragma unroll
-        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
-#pragma unroll
-        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J5_E2];
-#pragma unroll
-        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
-        if (cand) {
-#pragma unroll
-            for (int p = 0; p < G; ++p) {
-                T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); q = fma(o[p].rz, o[p].rz, q);
-                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
-#pragma unroll
-        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = y0[p] * t[p];                 // 1/sqrt(x)
+        group_fold_seeds<G>(r2, [&](int p) { return __double2hiint(s[p % W][IE]); }, [&](int p) { return rows[p / W][J5_E2]; },
+                            [&](int p) { T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); return fma(o[p].rz, o[p].rz, q); },
+                            x, y0);
+        group_rsqrt_step<G>(x, y0, T(1), T(0.5), T(0.375), t);                      // 1/sqrt(x)
 #pragma unroll
         for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];
 #pragma unroll
@@ -360,45 +321,21 @@ template <typename T> struct AccJerkOp {
 #pragma unroll 1
             for (int z = 0; z < ((MODE & 1) ? one : 1); ++z) chains();       // block 1a
         }
+        T x[G], t[G], h[G];
         if (FOLD) {
-            // x = ((e2_i + rx^2) + ry^2 + rz^2) + e2_j: 31 FP64 instructions per pair.  The chain no longer
-            // holds the bare r2 the mask is read from (r2 zero or denormal: the pair of a particle with
-            // itself, coincident particles), so the group tests a NECESSARY condition -- the high word of
-            // the chain still equals that of e2_i: r2 < 2^-20 e2_i, or both zero -- with one chained
-            // compare per pair, and only a group with such a pair forms r2 again and zeroes the seeds of
-            // the pairs the mask really applies to (rsqrt_seed_masked's test).  A particle meets itself
-            // once per sweep, close pairs inside 1e-3 softening lengths are as rare.
-            bool cand = false;
-#pragma unroll
-            for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
-#pragma unroll
-            for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x
-#pragma unroll
-            for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(e[p]));
-            if (cand) {
-#pragma unroll
-                for (int p = 0; p < G; ++p) {
-                    T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); q = fma(o[p].rz, o[p].rz, q);
-                    if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
-                }
-            }
+            // x = ((e2_i + rx^2) + ry^2 + rz^2) + e2_j: 31 FP64 instructions per pair; the mask per group
+            // (group_fold_seeds, common.cuh)
+            group_fold_seeds<G>(r2, [&](int p) { return __double2hiint(s[p % W][IE]); }, [&](int p) { return e[p]; },
+                                [&](int p) { T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); return fma(o[p].rz, o[p].rz, q); },
+                                x, y0);
         } else {
 #pragma unroll
-            for (int p = 0; p < G; ++p) e[p] = r2[p] + e[p];                 // x = r2 + e2
+            for (int p = 0; p < G; ++p) x[p] = r2[p] + e[p];                 // x = r2 + e2
 #pragma unroll
-            for (int p = 0; p < G; ++p) y0[p] = rsqrt_seed_masked<false>(e[p], r2[p]);
+            for (int p = 0; p < G; ++p) y0[p] = rsqrt_seed_masked<false>(x[p], r2[p]);
         }
-        T t[G], h[G];
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = e[p] * y0[p];
-#pragma unroll
-        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.64951905283832900), T(0.86602540378443865));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1.7320508075688772));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = y0[p] * t[p];                 // sqrt(3/x)
+        // sqrt(3/x): k = sqrt 3, k/2, 3k/8
+        group_rsqrt_step<G>(x, y0, T(1.7320508075688772), T(0.86602540378443865), T(0.64951905283832900), t);
 #pragma unroll
         for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];                  // 3/x
 #pragma unroll
@@ -727,30 +664,9 @@ template <typename T> struct TstepOp {
 #pragma unroll
             for (int p = 0; p < G; ++p) { r2[p] = fma(rz[p], rz[p], r2[p]); rv[p] = fma(rz[p], vz[p], rv[p]); }
         }
-        bool cand = false;
-#pragma unroll
-        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
-#pragma unroll
-        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J8_E2];
-#pragma unroll
-        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
-        if (cand) {
-#pragma unroll
-            for (int p = 0; p < G; ++p) {
-                T q = rx[p] * rx[p]; q = fma(ry[p], ry[p], q); q = fma(rz[p], rz[p], q);
-                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
-#pragma unroll
-        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = y0[p] * t[p];                 // 1/r
+        group_fold_seeds<G>(r2, [&](int p) { return __double2hiint(s[p % W][IE]); }, [&](int p) { return rows[p / W][J8_E2]; },
+                            [&](int p) { T q = rx[p] * rx[p]; q = fma(ry[p], ry[p], q); return fma(rz[p], rz[p], q); }, x, y0);
+        group_rsqrt_step<G>(x, y0, T(1), T(0.5), T(0.375), t);                      // 1/r
 #pragma unroll
         for (int p = 0; p < G; ++p) h[p] = t[p] * t[p];                  // 1/r^2
         // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv   (pair())
@@ -859,30 +775,12 @@ template <typename T> struct NregXOp {
         for (int p = 0; p < G; ++p) r2[p] = fma(o[p].ry, o[p].ry, r2[p]);
 #pragma unroll
         for (int p = 0; p < G; ++p) r2[p] = fma(o[p].rz, o[p].rz, r2[p]);
-        bool cand = false;
+        group_fold_seeds<G>(r2, [&](int p) { return __double2hiint(s[p % W][IE]); }, [&](int p) { return rows[p / W][J8_E2]; },
+                            [&](int p) { T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); return fma(o[p].rz, o[p].rz, q); },
+                            x, y0);
+        group_rsqrt_step<G>(x, y0, T(1), T(0.5), T(0.375), t);
 #pragma unroll
-        for (int p = 0; p < G; ++p) cand = cand || (__double2hiint(r2[p]) == __double2hiint(s[p % W][IE]));
-#pragma unroll
-        for (int p = 0; p < G; ++p) x[p] = r2[p] + rows[p / W][J8_E2];
-#pragma unroll
-        for (int p = 0; p < G; ++p) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[p]) : "d"(x[p]));
-        if (cand) {
-#pragma unroll
-            for (int p = 0; p < G; ++p) {
-                T q = o[p].rx * o[p].rx; q = fma(o[p].ry, o[p].ry, q); q = fma(o[p].rz, o[p].rz, q);
-                if ((unsigned)__double2hiint(q) < 0x00100000u) y0[p] = T(0);
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = x[p] * y0[p];
-#pragma unroll
-        for (int p = 0; p < G; ++p) h[p] = fma(-t[p], y0[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], T(0.375), T(0.5));
-#pragma unroll
-        for (int p = 0; p < G; ++p) t[p] = fma(h[p], t[p], T(1));
-#pragma unroll
-        for (int p = 0; p < G; ++p) o[p].r1 = y0[p] * t[p];
+        for (int p = 0; p < G; ++p) o[p].r1 = t[p];
 #pragma unroll
         for (int p = 0; p < G; ++p) h[p] = o[p].r1 * o[p].r1;
 #pragma unroll
