@@ -229,7 +229,11 @@ int tupan_cuda_abs_min_dev(long long n, const void *d_values, void *d_min, void 
 int tupan_cuda_init(void);                         /* create the context on the current device */
 int tupan_cuda_last_error(char *msg, int msg_len); /* code of the last failure (0 = none) */
 void tupan_cuda_clear_error(void);
-/* force a launch shape (tests/tuning): lane_split < 0 restores the heuristic */
+/* force a launch shape (tests/tuning): lane_split < 0 restores the heuristic.
+ * lane_split: 0 = several particles per thread, lanes independent (for the fp64 kernels with a grouped
+ * form: its first group shape); 1 = 2^js_log2 lanes of a warp share a particle; 2 = as 0 with the
+ * kernel's second, smaller group shape (acc_jerk, acc, tstep, nreg_X in fp64; other kernels run 0).
+ * jg = number of j chunks (> 1: raw accumulators go through a workspace and a finalize launch). */
 void tupan_cuda_force_plan(int lane_split, int js_log2, int jg);
 void tupan_cuda_last_plan(int *lane_split, int *js_log2, int *jg);
 /* the launch shape the cost model picks for `kernel` on ni x nj pairs (no device needed) */
