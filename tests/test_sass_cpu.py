@@ -23,7 +23,7 @@ EXPECT = {
     "pair_kernel_grouped<tupan::AccJerkOp<double>, 256, 2, 4, 27, 128, 4, false>": (1, 31.0, 3.6, 6.8),
     "pair_kernel_grouped<tupan::AccOp<double>, 256, 6, 2, 8, 128, 4, false>": (1, 18.0, 1.1, 5.0),
     "pair_kernel_grouped<tupan::PhiOp<double>, 256, 3, 2, 8, 128, 4, false>": (1, 13.0, 0.8, 6.0),
-    "pair_kernel_grouped<tupan::TstepOp<double>, 256, 3, 2, 8, 128, 4, false>": (2, 36.0, 3.0, 14.0),
+    "pair_kernel_grouped<tupan::TstepOp<double>, 256, 3, 2, 8, 128, 4, false>": (2, 36.0, 3.0, 13.0),
     "pair_kernel_grouped<tupan::NregXOp<double>, 256, 4, 2, 8, 128, 4, false>": (1, 28.0, 2.3, 6.0),
     "pair_kernel_grouped<tupan::SnapCrackleOp<double>, 256, 1, 4, 1, 128, 4, false>": (1, 78.0, 10.0, 15.0),
 }

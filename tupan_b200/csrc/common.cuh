@@ -186,6 +186,32 @@ TUPAN_DEV void group_rsqrt_step(const T (&x)[G], const T (&y0)[G], T k0, T k1, T
     for (int p = 0; p < G; ++p) y[p] = y0[p] * t[p];
 }
 
+// k/sqrt(x) for an x >= 0 whose zero must give a FINITE result rather than a masked one (tstep's second
+// seed: x = w2 is exactly 0 for a masked pair, and so is the factor the result scales).  One integer
+// minimum clamps the seed's high word at 2^511 = rsqrt(2^-1022), the seed of the smallest normal x, instead
+// of the compare + select of rsqrt_seed_masked: every normal x keeps its seed, x = 0 (seed +inf) gets
+// 2^511, and 0 * (2^511 k) = 0 downstream.  The low word keeps the raw high bits, as with CLEAN = false.
+TUPAN_DEV double rsqrt_scaled_clamped(double x, double k0, double k1, double k2)
+{
+    double y0;
+    asm("{\n"
+        ".reg .f64 y;\n"
+        ".reg .b32 yl, yh, yc;\n"
+        "rsqrt.approx.ftz.f64 y, %1;\n"
+        "mov.b64 {yl, yh}, y;\n"
+        "min.u32 yc, yh, 0x5fe00000;\n"
+        "mov.b64 %0, {yh, yc};\n"
+        "}\n"
+        : "=d"(y0)
+        : "d"(x));
+    const double t = x * y0;
+    const double h = fma(-t, y0, 1.0);
+    const double p = fma(h, k2, k1);
+    const double c = fma(h, p, k0);
+    return y0 * c;
+}
+TUPAN_DEV float rsqrt_scaled_clamped(float x, float k0, float k1, float k2) { return rsqrt_scaled<false>(x, x, k0, k1, k2); }
+
 template <typename T> struct InvR { T r1, r2, r3; };
 
 // x = r2 + e2 (softened).  Returns 1/r, 1/r^2, 1/r^3 of the softened distance, all 0 when the

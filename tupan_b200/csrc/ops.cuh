@@ -598,15 +598,16 @@ template <typename T> struct TstepOp {
         T v2 = vx * vx; v2 = fma(vy, vy, v2); v2 = fma(vz, vz, v2);
         // CLEAN = false (the seed's low word is not zeroed: one MOV less per rsqrt): a masked pair gets
         // r1 ~ 1e-314 instead of 0, whose square r2inv underflows to exactly 0, so w2 = 0 * (v2 + phi2) = 0
-        // and gamma = 0 * (...) = 0 as before; w2 = 0 masks the second seed by its own exponent, and
-        // 0 * (a denormal) = 0.
+        // and gamma = 0 * (...) = 0 as before; the second seed, of w2 = 0, is clamped to a finite value,
+        // and 0 * (a finite number) = 0.
         InvR<T> w = soft_inv<false>(x, r2);
         // w2 = (v2 + 2 phi)/r2 ; gamma = (w2 + 2 phi/r2)/r2 * eta/sqrt(w2) ; w2 -= gamma*rv
         T phi2 = m2 * w.r1;
         T w2 = w.r2 * (v2 + phi2);
         T gamma = w.r2 * fma(w.r2, phi2, w2);
-        // masked pair: w2 is exactly 0, its own exponent masks the seed -> gamma 0 -> w2 stays 0
-        gamma *= rsqrt_scaled<false>(w2, w2, p.eta, p.eta_k1, p.eta_k2);
+        // masked pair: w2 is exactly 0 and so is gamma; the seed of 0 is clamped to a finite value
+        // (rsqrt_scaled_clamped), gamma stays 0 -> w2 stays 0
+        gamma *= rsqrt_scaled_clamped(w2, p.eta, p.eta_k1, p.eta_k2);
         w2 = fma(-gamma, rv, w2);
         a[0] += w2;
         a[1] = rmax_nonneg(a[1], w2);
@@ -625,7 +626,7 @@ template <typename T> struct TstepOp {
     // ---- grouped form (pair_kernel_grouped, fp64; see AccJerkOp): 36 FP64 instructions per pair instead
     // of 37 (e2_i in the r2 chain, the r2 mask tested per group); the r2 and r.v chains step by step in a
     // block of their own -- fma(ry, ry, r2) next to fma(ry, vy, rv), which finds ry in the operand-reuse
-    // cache.  The second seed keeps its per-pair mask (w2's own exponent).
+    // cache.  The second seed needs no mask, only a clamp (rsqrt_scaled_clamped).
     // Measured (profiles/r02_kernel_lab6_tstep.txt, tools/kernel_lab3.cu -DLAB_OP=3): ungrouped 394.8 Gpair/s (94.3 clocks
     // per pair), 3 x 2 429.2 (86.7), 4 x 2 427.1, 2 x 2 406.2 (the second shape, 512 particles per CTA).
 #ifndef TUPAN_TSTEP_GROUPED
@@ -681,7 +682,7 @@ template <typename T> struct TstepOp {
 #pragma unroll
         for (int p = 0; p < G; ++p) t[p] = h[p] * t[p];                  // gamma without the eta/sqrt(w2)
 #pragma unroll
-        for (int p = 0; p < G; ++p) h[p] = rsqrt_scaled<false>(v2[p], v2[p], prm.eta, prm.eta_k1, prm.eta_k2);
+        for (int p = 0; p < G; ++p) h[p] = rsqrt_scaled_clamped(v2[p], prm.eta, prm.eta_k1, prm.eta_k2);
 #pragma unroll
         for (int p = 0; p < G; ++p) t[p] = t[p] * h[p];
 #pragma unroll
